@@ -1,0 +1,508 @@
+/*
+ * oracle.c -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * Stream-form CPU restatement of the reference algorithms.  Each function
+ * names the reference lines it follows (paths relative to /root/reference).
+ * Compiled with -ffp-contract=off: the single FMA the reference's own Release
+ * build fuses (multifm/fast_atan2f.c:131 under gcc -O3 -march=<fma capable>)
+ * is selected explicitly through the `fma` argument.
+ */
+#include "oracle.h"
+
+#include <complex.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define Q14_SHIFT 14    /* filter/filter.h:16 -- "Q_15_SHIFT" is 14 */
+
+/* filter/complex.h:31-34: (a >> 14) + ((a >> 13) & 1), truncated to int16 by the return type */
+static inline int16_t rq(int32_t a)
+{
+    return (int16_t)((a >> Q14_SHIFT) + ((a >> (Q14_SHIFT - 1)) & 1));
+}
+
+/* all accumulations wrap modulo 2^32 like x86 int32 arithmetic does */
+static inline int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+static inline int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+static inline int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+
+/* ---------------------------------------------------------------------- */
+/* a1  multifm/demod.c:205-261, multifm/receiver.c:220, filter/direct_fir.c:72-83 */
+/* ---------------------------------------------------------------------- */
+void orc_prepare_taps(const double *lpf, size_t nr_taps, int32_t offset_hz, uint32_t sample_rate,
+                      double gain, int16_t *c_re, int16_t *c_im)
+{
+    const double w = -2.0 * M_PI * (double)offset_hz / (double)sample_rate;     /* demod.c:210 */
+    for (size_t i = 0; i < nr_taps; i++) {
+        const double complex t = gain * cexp(CMPLX(0, w * (double)i)) * lpf[i];  /* demod.c:234 */
+        c_re[i] = (int16_t)(creal(t) * 16384.0);                                 /* demod.c:242 */
+        c_im[i] = (int16_t)(cimag(t) * 16384.0);                                 /* demod.c:243 */
+    }
+}
+
+void orc_derot_incr(int32_t offset_hz, uint32_t sample_rate, unsigned decimation, int16_t incr[2])
+{
+    const double fwt0 = 2.0 * M_PI * (double)offset_hz / (double)sample_rate;    /* direct_fir.c:73 */
+    const double complex d = cexp(CMPLX(0, -fwt0 * (double)decimation));         /* direct_fir.c:75 */
+    incr[0] = (int16_t)(int32_t)(creal(d) * 16384.0);                            /* direct_fir.c:76 */
+    incr[1] = (int16_t)(int32_t)(cimag(d) * 16384.0);                            /* direct_fir.c:77 */
+}
+
+double orc_db_to_gain(double db)
+{
+    return pow(10.0, db / 10.0);                                                 /* receiver.c:220 */
+}
+
+/* ---------------------------------------------------------------------- */
+/* a4  multifm/fast_atan2f.c:15-81 (table), :101-174; multifm/fm_demod.c:36-85 */
+/* ---------------------------------------------------------------------- */
+static float g_atan_tab[257];
+static int g_atan_tab_ready;
+
+/* The reference table holds atan(i/255), i = 0..255, written with 7 significant
+ * decimal digits ("%.6e") and one duplicated guard entry; regenerating it that
+ * way is bit-identical (checked against the reference in tests). */
+void orc_atan_table(float tab[257])
+{
+    for (int i = 0; i < 257; i++) {
+        char txt[32];
+        int j = i > 255 ? 255 : i;
+        snprintf(txt, sizeof(txt), "%.6e", atan((double)j / 255.0));
+        tab[i] = strtof(txt, NULL);
+    }
+}
+
+float orc_fast_atan2f(float y, float x, int fma)
+{
+    if (!g_atan_tab_ready) { orc_atan_table(g_atan_tab); g_atan_tab_ready = 1; }
+
+    const float ya = fabsf(y), xa = fabsf(x);
+    float z, base;
+
+    if (!(ya > 0.0f || xa > 0.0f)) return 0.0f;                 /* :113 */
+    z = (ya < xa) ? ya / xa : xa / ya;                          /* :116-119 */
+
+    if ((double)z < 0.003921569) {                              /* :123, double compare */
+        base = z;
+    } else {
+        float alpha = z * 255.0f;                               /* :127 */
+        int idx = ((int)alpha) & 0xff;                          /* :128 */
+        alpha -= (float)idx;                                    /* :129 */
+        float lo = g_atan_tab[idx];
+        float d = g_atan_tab[idx + 1] - g_atan_tab[idx];
+        base = fma ? fmaf(d, alpha, lo) : (lo + d * alpha);     /* :132-133 */
+    }
+
+    const float pi_f = (float)3.14159265358979323846;
+    const float hpi_f = (float)1.57079632679489661923;
+    float angle;
+    if (xa > ya) {                                              /* :136 */
+        if (x >= 0.0f) angle = (y >= 0.0f) ? base : -base;
+        else           angle = (y >= 0.0f) ? (pi_f - base) : (base - pi_f);
+    } else {
+        if (y >= 0.0f) angle = (x >= 0.0f) ? (hpi_f - base) : (hpi_f + base);
+        else           angle = (x >= 0.0f) ? (-hpi_f + base) : (-hpi_f - base);
+    }
+    return angle;
+}
+
+int16_t orc_fm_pcm(int32_t s_re, int32_t s_im, int fma)
+{
+    float phi = orc_fast_atan2f((float)s_im, (float)s_re, fma); /* fm_demod.c:68 */
+    float scaled = (float)(((double)phi / M_PI) * (double)16384.0f); /* fm_demod.c:71 */
+    return (int16_t)scaled;                                     /* fm_demod.c:72 */
+}
+
+/* ---------------------------------------------------------------------- */
+/* a2-a4  filter/direct_fir.c:329-417 + :152-172, multifm/fm_demod.c:53-77 */
+/* ---------------------------------------------------------------------- */
+void orc_chan_state_init(orc_chan_state *st, int32_t offset_hz, uint32_t sample_rate, unsigned decimation)
+{
+    int16_t incr[2];
+    memset(st, 0, sizeof(*st));
+    orc_derot_incr(offset_hz, sample_rate, decimation, incr);
+    st->incr_re = incr[0]; st->incr_im = incr[1];
+    st->rot_re = 16384; st->rot_im = 0;                         /* direct_fir.c:78-79 */
+}
+
+size_t orc_chan_stream(orc_chan_state *st, size_t nr_taps, const int16_t *c_re, const int16_t *c_im,
+                       unsigned decimation, const int16_t *iq, size_t n, int fma,
+                       int16_t *out_iq, int16_t *out_pcm)
+{
+    if (n < nr_taps) return 0;
+    const size_t K = (n - nr_taps) / decimation + 1;
+    const int derotate = !(st->incr_re == 0 && st->incr_im == 0);   /* direct_fir.c:406 */
+
+    for (size_t k = 0; k < K; k++) {
+        const int16_t *x = iq + 2 * k * (size_t)decimation;
+        int32_t acc_re = 0, acc_im = 0;
+        for (size_t i = 0; i < nr_taps; i++) {                  /* direct_fir.c:366-385 */
+            int32_t s_re = x[2 * i], s_im = x[2 * i + 1], t_re = c_re[i], t_im = c_im[i];
+            acc_re = wadd(acc_re, wsub(wmul(t_re, s_re), wmul(t_im, s_im)));
+            acc_im = wadd(acc_im, wadd(wmul(t_re, s_im), wmul(t_im, s_re)));
+        }
+        if (derotate) {                                         /* direct_fir.c:406-409, :162-167 */
+            int32_t q_re = rq(acc_re), q_im = rq(acc_im);
+            int32_t r_re = st->rot_re, r_im = st->rot_im, i_re = st->incr_re, i_im = st->incr_im;
+            acc_re = wsub(wmul(q_re, r_re), wmul(q_im, r_im));
+            acc_im = wadd(wmul(q_re, r_im), wmul(q_im, r_re));
+            st->rot_re = rq(wsub(wmul(r_re, i_re), wmul(r_im, i_im)));
+            st->rot_im = rq(wadd(wmul(r_re, i_im), wmul(r_im, i_re)));
+            st->rot_counter++;
+        }
+        const int32_t y_re = rq(acc_re), y_im = rq(acc_im);     /* direct_fir.c:412-413 */
+        if (out_iq) { out_iq[2 * k] = (int16_t)y_re; out_iq[2 * k + 1] = (int16_t)y_im; }
+
+        /* fm_demod.c:55-64: s = y * conj(last) */
+        const int32_t b_re = st->last_re, b_im = -st->last_im;
+        const int32_t s_re = wsub(wmul(y_re, b_re), wmul(y_im, b_im));
+        const int32_t s_im = wadd(wmul(y_re, b_im), wmul(y_im, b_re));
+        if (out_pcm) out_pcm[k] = orc_fm_pcm(s_re, s_im, fma);
+        st->last_re = y_re; st->last_im = y_im;
+    }
+    return K;
+}
+
+/* ---------------------------------------------------------------------- */
+/* a5  filter/polyphase_fir.c:47-105,162-233; filter/utils.c:46-116         */
+/* ---------------------------------------------------------------------- */
+int orc_resamp_init(orc_resamp *r, const int16_t *taps, size_t nr_taps, unsigned interp, unsigned decim)
+{
+    memset(r, 0, sizeof(*r));
+    if (!nr_taps || !interp || !decim) return -1;
+    size_t m = (nr_taps + interp - 1) / interp;                 /* polyphase_fir.c:70 */
+    m = (m + 3) & ~(size_t)3;                                   /* polyphase_fir.c:73 */
+    r->phase_filters = calloc((size_t)interp * m, sizeof(int16_t));
+    if (!r->phase_filters) return -1;
+    for (size_t i = 0; i < nr_taps; i++)                        /* polyphase_fir.c:81-83 */
+        r->phase_filters[(i % interp) * m + i / interp] = taps[i];
+    r->interp = interp; r->decim = decim; r->phase_len = m; r->phase = 0;
+    return 0;
+}
+
+void orc_resamp_free(orc_resamp *r)
+{
+    free(r->phase_filters);
+    r->phase_filters = NULL;
+}
+
+size_t orc_resamp_stream(orc_resamp *r, const int16_t *x, size_t n, int16_t *out, size_t cap, size_t *consumed)
+{
+    size_t off = 0, produced = 0;
+    const size_t m = r->phase_len;
+    while (produced < cap && off < n && (n - off) > m) {        /* polyphase_fir.c:184, strict '>' */
+        const int16_t *h = r->phase_filters + r->phase * m;
+        int32_t acc = 0;
+        for (size_t j = 0; j < m; j++)                          /* utils.c:88-93 */
+            acc = wadd(acc, wmul((int32_t)x[off + j], (int32_t)h[j]));
+        out[produced++] = rq(acc);                              /* utils.c:109 */
+        size_t p = r->phase + r->decim;                         /* polyphase_fir.c:206-211 */
+        off += p / r->interp;
+        r->phase = p % r->interp;
+    }
+    *consumed = off;
+    return produced;
+}
+
+/* ---------------------------------------------------------------------- */
+/* a7  pager/bch_code.c:42-74 (field), :307-398 (decode); poly per          */
+/*     pager/pager_pocsag.c:150 : x^5 + x^2 + 1, n=31, k=21, t=2            */
+/* ---------------------------------------------------------------------- */
+static int g_exp[32], g_log[32], g_gf_ready;
+
+static void gf_init(void)
+{
+    /* alpha^i in polynomial form; log(0) = -1 */
+    int v = 1;
+    for (int i = 0; i < 31; i++) {
+        g_exp[i] = v; g_log[v] = i;
+        v <<= 1;
+        if (v & 0x20) v ^= 0x25;        /* x^5 = x^2 + 1 */
+    }
+    g_exp[31] = 0;                      /* never indexed with 31 after a % 31 */
+    g_log[0] = -1;
+    g_gf_ready = 1;
+}
+
+int orc_bch_decode(uint32_t *word)
+{
+    if (!g_gf_ready) gf_init();
+    uint32_t r = *word;
+    int s[5], any = 0, fail = 0;
+
+    for (int i = 1; i <= 4; i++) {                              /* bch_code.c:325-340 */
+        int v = 0;
+        for (int j = 0; j < 31; j++)
+            if ((r >> (30 - j)) & 1) v ^= g_exp[(i * j) % 31];
+        if (v) any = 1;
+        s[i] = g_log[v];
+    }
+
+    if (any) {
+        if (s[1] != -1) {
+            const int s3 = (s[1] * 3) % 31;
+            if (s[3] == s3) {                                   /* single error, :345-347 */
+                r ^= 1u << (30 - s[1]);
+            } else {                                            /* two errors, :353-388 */
+                int aux = (s[3] != -1) ? (g_exp[s3] ^ g_exp[s[3]]) : g_exp[s3];
+                int reg1 = (s[2] - g_log[aux] + 31) % 31;
+                int reg2 = (s[1] - g_log[aux] + 31) % 31;
+                int loc[3], count = 0;
+                for (int i = 1; i <= 31; i++) {                 /* Chien search */
+                    int q = 1;
+                    reg1 = (reg1 + 1) % 31; q ^= g_exp[reg1];
+                    reg2 = (reg2 + 2) % 31; q ^= g_exp[reg2];
+                    if (!q && count < 3) loc[count++] = i % 31;
+                }
+                if (count == 2) {
+                    r ^= 1u << (30 - loc[0]);
+                    r ^= 1u << (30 - loc[1]);
+                } else {
+                    fail = 1;
+                }
+            }
+        } else if (s[2] != -1) {                                /* :389-391 */
+            fail = 1;
+        }
+    }
+    *word = r;
+    return fail;
+}
+
+/* ---------------------------------------------------------------------- */
+/* a6/a7  pager/pager_pocsag.c:82-117 (eye), :242-297 (deliver),            */
+/*        :320-432 (batch), :434-543 (FSM)                                  */
+/* ---------------------------------------------------------------------- */
+#define POCSAG_SYNC 0x7cd215d8u     /* pager_pocsag_priv.h:40 */
+#define POCSAG_IDLE 0x6983915eu     /* pager_pocsag_priv.h:46 (bit-reversed standard idle) */
+
+enum { ST_SEARCH = 0, ST_SYNCHRONIZED = 1, ST_BATCH = 2, ST_SYNCWORD = 3 };
+enum { MT_NONE = 0, MT_UNKNOWN = 1, MT_ALPHA = 2, MT_NUMERIC = 3 };
+
+struct eye {
+    uint32_t spb, baud, cur, matches;
+    uint32_t reg[75];
+};
+
+struct orc_pocsag {
+    int state;
+    uint16_t sample_skip, baud;
+    /* batch */
+    uint16_t b_skip, b_word, b_word_bit, b_bits;
+    uint32_t batch[16];
+    /* sync search */
+    uint16_t s_skip;
+    size_t s_bits;
+    uint32_t s_word;
+    struct eye eyes[3];
+    /* message under assembly */
+    char alpha[512], numeric[512];
+    size_t n_alpha, n_numeric;
+    int score;
+    int seen_nonprint;
+    uint32_t capcode, w_alpha, w_numeric;
+    size_t vb_alpha, vb_numeric;
+    uint8_t function;
+    int msg_type;
+    /* sink */
+    orc_msg *msgs;
+    size_t cap, n;
+};
+
+static int sync_ok(uint32_t w) { return __builtin_popcount(w ^ POCSAG_SYNC) <= 4; }
+
+static void eyes_reset(orc_pocsag *p)
+{
+    static const uint32_t spb[3] = { 75, 32, 16 }, baud[3] = { 512, 1200, 2400 };
+    for (int i = 0; i < 3; i++) {
+        memset(&p->eyes[i], 0, sizeof(p->eyes[i]));
+        p->eyes[i].spb = spb[i]; p->eyes[i].baud = baud[i];
+    }
+}
+
+static void msg_reset(orc_pocsag *p)
+{
+    p->n_alpha = p->n_numeric = 0;
+    p->w_alpha = p->w_numeric = 0;
+    p->vb_alpha = p->vb_numeric = 0;
+    p->seen_nonprint = 0; p->score = 0;
+    p->msg_type = MT_NONE; p->function = 0;
+}
+
+static void batch_reset(orc_pocsag *p)
+{
+    memset(p->batch, 0, sizeof(p->batch));
+    p->b_word = p->b_word_bit = p->b_skip = p->b_bits = 0;
+}
+
+orc_pocsag *orc_pocsag_new(size_t max_msgs)
+{
+    orc_pocsag *p = calloc(1, sizeof(*p));
+    p->msgs = calloc(max_msgs ? max_msgs : 1, sizeof(orc_msg));
+    p->cap = max_msgs;
+    eyes_reset(p);
+    msg_reset(p);
+    return p;
+}
+
+void orc_pocsag_delete(orc_pocsag *p)
+{
+    if (!p) return;
+    free(p->msgs);
+    free(p);
+}
+
+size_t orc_pocsag_msgs(orc_pocsag *p, orc_msg **msgs) { *msgs = p->msgs; return p->n; }
+size_t orc_msg_size(void) { return sizeof(orc_msg); }
+
+static void deliver(orc_pocsag *p)                              /* pager_pocsag.c:242-297 */
+{
+    if (p->msg_type == MT_NONE) return;
+    if (p->n_alpha != 0) {
+        char last = p->alpha[p->n_alpha - 1];
+        if (last == 0x4 || last == 0x3 || last == 0x0 || last == 0x17) p->score = 1;
+    }
+    if (p->n_numeric > 40) p->score = 1;
+    const int is_alpha = p->score > 0;
+    if (p->n < p->cap) {
+        orc_msg *m = &p->msgs[p->n++];
+        memset(m, 0, sizeof(*m));
+        m->kind = (uint32_t)is_alpha; m->baud = p->baud; m->capcode_lo = p->capcode; m->function = p->function;
+        if (is_alpha) { m->len = (uint32_t)p->n_alpha; memcpy(m->data, p->alpha, p->n_alpha); }
+        else          { m->len = (uint32_t)p->n_numeric; memcpy(m->data, p->numeric, p->n_numeric); }
+    }
+    msg_reset(p);
+}
+
+static void process_batch(orc_pocsag *p)                        /* pager_pocsag.c:320-432 */
+{
+    static const char bcd_map[16] = { '0','1','2','3','4','5','6','7','8','9','X','U',' ','-','[',']' };
+    for (unsigned z = 0; z < 16; z++) {
+        uint32_t w = p->batch[z] & 0x7fffffffu;
+        if (orc_bch_decode(&w)) {
+            if (p->msg_type != MT_NONE) deliver(p);
+            return;
+        }
+        if (w == POCSAG_IDLE) {
+            if (p->msg_type != MT_NONE) deliver(p);
+            continue;
+        }
+        if ((w & 1) == 0) {                                     /* address word, :356-363 */
+            deliver(p);
+            p->msg_type = MT_UNKNOWN;
+            p->function = (w >> 19) & 0x3;
+            p->capcode = (((w >> 1) & 0x3ffffu) << 3) + ((z >> 1) & 0x7);
+        } else if (p->msg_type == MT_UNKNOWN) {                 /* data word, :364-417 */
+            const uint32_t val = (w >> 1) & 0xfffffu;
+            p->w_alpha |= val << p->vb_alpha;
+            p->vb_alpha += 20;
+            while (p->vb_alpha >= 7) {
+                char c = (char)(p->w_alpha & 0x7f);
+                /* the reference writes message_alpha[] unchecked (512 bytes); we stop storing at 511 */
+                if (p->n_alpha < 511) p->alpha[p->n_alpha++] = c;
+                if ((c >= 0x20 && c <= 0x7e) || c == 0xa || c == 0xd) {     /* isprint() in the C locale */
+                    if (!p->seen_nonprint) p->score++;
+                } else {
+                    p->seen_nonprint = 1;
+                    if (c != 0x03 && c != 0x04 && c != 0x17 && c != 0x0) p->score -= 10;
+                }
+                p->w_alpha >>= 7;
+                p->vb_alpha -= 7;
+            }
+            if (p->n_numeric < 511) {
+                p->w_numeric |= val << p->vb_numeric;
+                p->vb_numeric += 20;
+                while (p->vb_numeric >= 4 && p->n_numeric < 511) {
+                    p->numeric[p->n_numeric++] = bcd_map[p->w_numeric & 0xf];
+                    p->w_numeric >>= 4;
+                    p->vb_numeric -= 4;
+                }
+            }
+        }
+    }
+}
+
+static void eye_on_sample(orc_pocsag *p, struct eye *e, int16_t sample)  /* pager_pocsag.c:82-117 */
+{
+    uint32_t *r = &e->reg[e->cur];
+    *r = (*r << 1) | (sample < 0 ? 1u : 0u);
+    if (sync_ok(*r)) {
+        e->matches++;
+    } else if (e->matches > e->spb / 2) {
+        p->sample_skip = (uint16_t)e->spb;
+        p->baud = (uint16_t)e->baud;
+        batch_reset(p);
+        p->b_skip = (uint16_t)(e->matches / 2);
+        p->state = ST_SYNCHRONIZED;
+    } else {
+        e->matches = 0;
+    }
+    e->cur = (e->cur + 1) % e->spb;
+}
+
+void orc_pocsag_on_pcm(orc_pocsag *p, const int16_t *pcm, size_t n)     /* pager_pocsag.c:434-543 */
+{
+    size_t i = 0;
+    while (i < n) {
+        switch (p->state) {
+        case ST_SEARCH:
+            while (i < n) {
+                eye_on_sample(p, &p->eyes[0], pcm[i]);
+                eye_on_sample(p, &p->eyes[1], pcm[i]);
+                eye_on_sample(p, &p->eyes[2], pcm[i]);
+                i++;
+                if (p->state == ST_SYNCHRONIZED) break;
+            }
+            break;
+        case ST_SYNCHRONIZED:
+            p->state = ST_BATCH;
+            /* fall through */
+        case ST_BATCH:
+            while (i < n) {
+                if (++p->b_skip == p->sample_skip) {
+                    uint32_t bit = pcm[i] < 0 ? 1u : 0u;
+                    /* `bit << bit_count` with bit_count up to 511: x86 masks the count to 5 bits */
+                    p->batch[p->b_word] |= bit << (p->b_bits & 31);
+                    p->b_word_bit++; p->b_bits++; p->b_skip = 0;
+                    if (p->b_word_bit == 32) {
+                        p->b_word_bit = 0;
+                        if (++p->b_word == 16) {
+                            process_batch(p);
+                            p->state = ST_SYNCWORD;
+                            p->b_word = 0;
+                            p->s_skip = 0; p->s_bits = 0; p->s_word = 0;
+                            i++;
+                            break;
+                        }
+                    }
+                }
+                i++;
+            }
+            break;
+        case ST_SYNCWORD:
+            while (i < n) {
+                if (++p->s_skip == p->sample_skip) {
+                    p->s_skip = 0;
+                    p->s_word = (p->s_word << 1) | (pcm[i] < 0 ? 1u : 0u);
+                    if (++p->s_bits == 32) {
+                        if (!sync_ok(p->s_word)) {
+                            p->state = ST_SEARCH;
+                            p->sample_skip = 0;
+                            eyes_reset(p);
+                            deliver(p);
+                        } else {
+                            p->state = ST_BATCH;
+                            batch_reset(p);
+                        }
+                        i++;
+                        break;
+                    }
+                }
+                i++;
+            }
+            break;
+        }
+    }
+}
