@@ -1,0 +1,118 @@
+/*
+ * tslb200_gpuchan.h -- C ABI of the B200 channel bank (CUDA layer).
+ *
+ * One gpuchan_t replaces the N per-channel `struct demod_thread` workers that the
+ * reference's receiver fans every IQ buffer out to:
+ *
+ *   reference seam                                    replaced by
+ *   ------------------------------------------------  --------------------------------
+ *   multifm/demod.c:205-261  _demod_fir_prepare       gpuchan_prepare_taps / gpuchan_create
+ *   filter/direct_fir.c:44-87 direct_fir_init         gpuchan_create (derotator increment)
+ *   multifm/receiver.c:78-98 receiver_sample_buf_deliver
+ *     -> multifm/demod.c:49-121 demod_thread_process  gpuchan_submit / gpuchan_submit_device
+ *        filter/direct_fir.c:422 direct_fir_process   (fused kernel: mix+FIR+decimate+derotate)
+ *        multifm/fm_demod.c:36 multifm_fm_demod_process (same kernel: discriminator)
+ *   multifm/demod.c:93 write(fifo_fd, out_buf, ...)   gpuchan_collect (int16 PCM per channel)
+ *   multifm/demod.c:75-81 signalDebugFile tap         gpuchan_collect_iq (GPUCHAN_F_KEEP_IQ)
+ *
+ * The stream contract is the reference's: output k of a channel is produced from input
+ * samples [k*D, k*D+T) as soon as they have been submitted; submits may have any length
+ * (4096-sample sample_bufs or megasample batches) and give identical output streams.
+ *
+ * Return convention is aresult_t compatible: 0 == A_OK, negative == error, FAILED(x) == (x != 0).
+ * Plain pointers and sizes only; no CUDA or torch types cross this boundary
+ * (a cudaStream_t travels as void *).
+ */
+#ifndef TSLB200_GPUCHAN_H
+#define TSLB200_GPUCHAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPUCHAN_OK            0
+#define GPUCHAN_E_NOMEM     (-1)
+#define GPUCHAN_E_BADARGS   (-2)
+#define GPUCHAN_E_BUSY      (-4)
+#define GPUCHAN_E_INVAL     (-5)
+#define GPUCHAN_E_CUDA      (-64)   /* a CUDA runtime call failed; see gpuchan_last_error() */
+#define GPUCHAN_E_NODEVICE  (-65)   /* no usable sm_100 device: there is NO CPU fallback */
+
+/* flags */
+#define GPUCHAN_F_ATAN_FMA   0x1u   /* fuse the one FMA gcc fuses in fast_atan2f.c:131 (reference Release build) */
+#define GPUCHAN_F_KEEP_IQ    0x2u   /* also keep the post-FIR int16 IQ (signalDebugFile tap) */
+#define GPUCHAN_F_DEFAULT    GPUCHAN_F_ATAN_FMA
+
+/* kernel selection (engine) */
+#define GPUCHAN_ENGINE_AUTO   0
+#define GPUCHAN_ENGINE_IMAD   1     /* exact int32 CUDA-core kernel */
+#define GPUCHAN_ENGINE_TC     2     /* exact int8-limb tcgen05 kernel */
+
+typedef struct gpuchan gpuchan_t;
+
+typedef struct gpuchan_cfg {
+    uint32_t struct_size;        /* = sizeof(gpuchan_cfg) */
+    uint32_t sample_rate_hz;     /* sampleRateHz      (multifm/receiver.c:139) */
+    uint32_t decimation;         /* decimationFactor  (multifm/receiver.c:160) */
+    uint32_t nr_taps;            /* lpfTaps length    (multifm/receiver.c:166-184) */
+    uint32_t nr_channels;        /* channels[] length (multifm/receiver.c:195) */
+    int32_t  device;             /* CUDA ordinal */
+    uint32_t max_batch_samples;  /* largest n_complex one submit may carry */
+    uint32_t flags;              /* GPUCHAN_F_* */
+    uint32_t engine;             /* GPUCHAN_ENGINE_* */
+    uint32_t reserved;
+    const double  *lpf_taps;     /* [nr_taps] real low-pass prototype, shared by all channels */
+    const int32_t *offset_hz;    /* [nr_channels] chanCenterFreq - centerFreqHz (multifm/receiver.c:229) */
+    const double  *gain;         /* [nr_channels] linear gain = 10^(dBGain/10) (receiver.c:220); NULL = 1.0 */
+} gpuchan_cfg;
+
+/* a1 on the host, in double with libm, exactly as the reference prepares taps. */
+int gpuchan_prepare_taps(const double *lpf_taps, size_t nr_taps, int32_t offset_hz, uint32_t sample_rate_hz,
+                         double gain, int16_t *c_re, int16_t *c_im);
+int gpuchan_derot_increment(int32_t offset_hz, uint32_t sample_rate_hz, uint32_t decimation, int16_t incr[2]);
+double gpuchan_db_to_gain(double db_gain);
+
+int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg);
+int gpuchan_destroy(gpuchan_t **ph);
+
+/* Append n_complex interleaved int16 I,Q samples from HOST memory (pinned or pageable) and launch the
+ * kernels for every output that became computable.  Asynchronous; iq_host may be reused after return
+ * only if it is pageable (pinned buffers must stay untouched until gpuchan_sync/collect). */
+int gpuchan_submit(gpuchan_t *h, const int16_t *iq_host, size_t n_complex);
+
+/* Same, with the samples already resident on h's device (e.g. after an NCCL broadcast).  Work is
+ * enqueued on cuda_stream (a cudaStream_t, NULL = the bank's own stream); d_iq must stay valid and
+ * unmodified until that stream reaches this point. */
+int gpuchan_submit_device(gpuchan_t *h, const int16_t *d_iq, size_t n_complex, void *cuda_stream);
+
+/* Wait for all submitted work. */
+int gpuchan_sync(gpuchan_t *h);
+
+/* Number of PCM samples per channel produced by the LAST submit (identical for all channels). */
+int gpuchan_pending(gpuchan_t *h, size_t *n_per_channel);
+
+/* Copy the last submit's PCM to host: channel c occupies pcm_host[c*cap_per_channel ... + n).
+ * Blocks until the data has arrived. */
+int gpuchan_collect(gpuchan_t *h, int16_t *pcm_host, size_t cap_per_channel, size_t *n_per_channel);
+/* Same for the post-FIR IQ tap (2 int16 per output); needs GPUCHAN_F_KEEP_IQ. */
+int gpuchan_collect_iq(gpuchan_t *h, int16_t *iq_host, size_t cap_per_channel, size_t *n_per_channel);
+
+/* Device view of the last submit's PCM for chaining on-GPU consumers (pager bank): channel c starts at
+ * d_pcm + c * pitch_samples. Valid until the next submit. */
+int gpuchan_device_pcm(gpuchan_t *h, const int16_t **d_pcm, size_t *pitch_samples, size_t *n_per_channel);
+
+/* Introspection for parity tests */
+int gpuchan_get_taps(gpuchan_t *h, uint32_t channel, int16_t *c_re, int16_t *c_im);
+int gpuchan_get_rot_state(gpuchan_t *h, uint32_t channel, int16_t rot[2], int16_t incr[2],
+                          uint64_t *outputs_so_far, uint32_t *cycle_mu, uint32_t *cycle_lambda);
+int gpuchan_engine(gpuchan_t *h);           /* engine actually in use */
+uint64_t gpuchan_kernel_launches(gpuchan_t *h);  /* kernels launched by this bank so far */
+const char *gpuchan_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSLB200_GPUCHAN_H */

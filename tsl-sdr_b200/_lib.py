@@ -1,0 +1,64 @@
+"""Loader for the C-ABI CUDA library.  No fallback: a missing library is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libtslb200.so")
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryMissing(
+                f"{LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is deliberately no CPU or PyTorch fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+class GpuChanCfg(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("sample_rate_hz", C.c_uint32), ("decimation", C.c_uint32),
+                ("nr_taps", C.c_uint32), ("nr_channels", C.c_uint32), ("device", C.c_int32),
+                ("max_batch_samples", C.c_uint32), ("flags", C.c_uint32), ("engine", C.c_uint32),
+                ("reserved", C.c_uint32), ("lpf_taps", C.POINTER(C.c_double)),
+                ("offset_hz", C.POINTER(C.c_int32)), ("gain", C.POINTER(C.c_double))]
+
+
+def _declare(L: C.CDLL) -> None:
+    vp, sz = C.c_void_p, C.c_size_t
+    L.gpuchan_prepare_taps.argtypes = [vp, sz, C.c_int32, C.c_uint32, C.c_double, vp, vp]
+    L.gpuchan_derot_increment.argtypes = [C.c_int32, C.c_uint32, C.c_uint32, vp]
+    L.gpuchan_db_to_gain.restype = C.c_double
+    L.gpuchan_db_to_gain.argtypes = [C.c_double]
+    L.gpuchan_create.argtypes = [C.POINTER(vp), C.POINTER(GpuChanCfg)]
+    L.gpuchan_destroy.argtypes = [C.POINTER(vp)]
+    L.gpuchan_submit.argtypes = [vp, vp, sz]
+    L.gpuchan_submit_device.argtypes = [vp, vp, sz, vp]
+    L.gpuchan_sync.argtypes = [vp]
+    L.gpuchan_pending.argtypes = [vp, C.POINTER(sz)]
+    L.gpuchan_collect.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.gpuchan_collect_iq.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.gpuchan_device_pcm.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
+    L.gpuchan_get_taps.argtypes = [vp, C.c_uint32, vp, vp]
+    L.gpuchan_get_rot_state.argtypes = [vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                        C.POINTER(C.c_uint32)]
+    L.gpuchan_engine.argtypes = [vp]
+    L.gpuchan_kernel_launches.restype = C.c_uint64
+    L.gpuchan_kernel_launches.argtypes = [vp]
+    L.gpuchan_last_error.restype = C.c_char_p
+
+
+# every symbol include/tslb200_gpuchan.h declares (checked by the CPU test-suite)
+EXPORTS = ["gpuchan_prepare_taps", "gpuchan_derot_increment", "gpuchan_db_to_gain", "gpuchan_create",
+           "gpuchan_destroy", "gpuchan_submit", "gpuchan_submit_device", "gpuchan_sync", "gpuchan_pending",
+           "gpuchan_collect", "gpuchan_collect_iq", "gpuchan_device_pcm", "gpuchan_get_taps",
+           "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error"]

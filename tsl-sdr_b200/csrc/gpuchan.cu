@@ -1,0 +1,721 @@
+/*
+ * gpuchan.cu -- B200 (sm_100a) channel bank: every narrow-band channel of a multifm receiver
+ * computed from one shared wide-band int16 IQ stream.  C ABI in include/tslb200_gpuchan.h.
+ *
+ * Kernels in this file (exact-integer CUDA-core engine, "IMAD"):
+ *   rot_cycle_detect_kernel   once per bank: transient length / period of each channel's derotator
+ *   rot_prepass_kernel        per submit: derotator phase at the start of every output tile
+ *   fir_fm_imad_kernel        per submit: mix+FIR+decimate (complex taps) -> derotate -> FM discriminator
+ *   carry_save_kernel         per submit: keep the < T input samples the next submit still needs
+ *
+ * Reference semantics reproduced bit for bit (paths relative to the reference tree):
+ *   filter/direct_fir.c:329-417  acc = sum_i c[i] * x[kD+i]   (int32, wraps), then rq -> derotate -> rq
+ *   filter/direct_fir.c:152-172  rot <- rq(rot * incr)         (lossy int16 recurrence, sequential)
+ *   multifm/fm_demod.c:36-85     s = y[k] * conj(y[k-1]);  pcm = (int16)(atan2(s)/pi * 16384)
+ *
+ * The complex tap x sample product uses the 3-multiplication form, which is exact modulo 2^32:
+ *   (c + jd)(a + jb):  P1 = c(a+b), P2 = a(d-c), P3 = b(c+d);  re = P1 - P3, im = P1 + P2.
+ */
+#include "../../include/tslb200_gpuchan.h"
+#include "fm_math.cuh"
+
+#include <cuda_runtime.h>
+
+#include <complex>
+#include <cstdarg>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace tslb200;
+
+/* ------------------------------------------------------------------------------------------ */
+/* error plumbing                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+static thread_local std::string g_last_error;
+
+static int set_err(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return set_err(GPUCHAN_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,         \
+                           cudaGetErrorString(_e));                                             \
+    } while (0)
+
+extern "C" const char *gpuchan_last_error(void) { return g_last_error.c_str(); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* a1: host-side tap preparation (double + libm, like the reference)                          */
+/* ------------------------------------------------------------------------------------------ */
+extern "C" int gpuchan_prepare_taps(const double *lpf_taps, size_t nr_taps, int32_t offset_hz,
+                                    uint32_t sample_rate_hz, double gain, int16_t *c_re, int16_t *c_im)
+{
+    if (!lpf_taps || !nr_taps || !sample_rate_hz || !c_re || !c_im) return set_err(GPUCHAN_E_BADARGS, "bad args");
+    /* multifm/demod.c:210 -- f_offs = -2*pi*offset/fs ; :234 tap = gain * e^{j f_offs i} * lpf[i] ;
+     * :242-243 (int16_t)(component * 2^14), C cast = truncation toward zero */
+    const double w = -2.0 * M_PI * (double)offset_hz / (double)sample_rate_hz;
+    for (size_t i = 0; i < nr_taps; i++) {
+        const std::complex<double> rot = std::exp(std::complex<double>(0.0, w * (double)i));
+        /* C99 (double * complex) * double evaluates component-wise: (gain*re)*lpf, (gain*im)*lpf */
+        const double re = (gain * rot.real()) * lpf_taps[i];
+        const double im = (gain * rot.imag()) * lpf_taps[i];
+        c_re[i] = (int16_t)(re * 16384.0);
+        c_im[i] = (int16_t)(im * 16384.0);
+    }
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_derot_increment(int32_t offset_hz, uint32_t sample_rate_hz, uint32_t decimation, int16_t incr[2])
+{
+    if (!sample_rate_hz || !decimation || !incr) return set_err(GPUCHAN_E_BADARGS, "bad args");
+    /* filter/direct_fir.c:73-77 */
+    const double fwt0 = 2.0 * M_PI * (double)offset_hz / (double)sample_rate_hz;
+    const std::complex<double> d = std::exp(std::complex<double>(0.0, -fwt0 * (double)decimation));
+    incr[0] = (int16_t)(int32_t)(d.real() * 16384.0);
+    incr[1] = (int16_t)(int32_t)(d.imag() * 16384.0);
+    return GPUCHAN_OK;
+}
+
+extern "C" double gpuchan_db_to_gain(double db_gain)
+{
+    return pow(10.0, db_gain / 10.0);   /* multifm/receiver.c:220 (power-dB formula used as amplitude) */
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* device code                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+namespace {
+
+constexpr int FIR_WARPS   = 8;       /* warps doing the FIR contraction */
+constexpr int CTA_THREADS = (FIR_WARPS + 1) * 32;   /* + 1 warp expanding the derotator sequence */
+constexpr int ROT_LMAX    = 4096;    /* longest derotator limit cycle we tabulate */
+constexpr uint32_t ROT_BUDGET = 1u << 24;   /* cycle-detection step budget per channel */
+
+/* logical input stream of one submit = [carry | fresh]; out-of-range reads are zero */
+struct InWindow {
+    const int *carry;   /* packed (re | im << 16) */
+    const int *fresh;
+    long long carry_len;
+    long long total;    /* carry_len + fresh_len */
+};
+
+__device__ __forceinline__ int in_sample(const InWindow &w, long long s)
+{
+    if (s < 0 || s >= w.total) return 0;
+    return (s < w.carry_len) ? __ldg(w.carry + s) : __ldg(w.fresh + (s - w.carry_len));
+}
+
+/* -------------------------------------------------------------------------------------- */
+/* Derotator recurrence analysis: the map rot -> rq(rot*incr) acts on a finite set, so every
+ * orbit is eventually periodic.  Brent's algorithm finds transient mu and period lambda. */
+__global__ void rot_cycle_detect_kernel(const int *__restrict__ incr, int nr_channels, uint32_t *__restrict__ mu_out,
+                                        uint32_t *__restrict__ lambda_out, int *__restrict__ cyc /* [C][ROT_LMAX] */)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nr_channels) return;
+    const int i_re = lo16(incr[c]), i_im = hi16(incr[c]);
+    uint32_t steps = 0, power = 1, lam = 1;
+    int t_re = 16384, t_im = 0, h_re = 16384, h_im = 0;
+    rot_step(h_re, h_im, i_re, i_im);
+    bool ok = true;
+    while (t_re != h_re || t_im != h_im) {
+        if (power == lam) { t_re = h_re; t_im = h_im; power <<= 1; lam = 0; }
+        rot_step(h_re, h_im, i_re, i_im);
+        lam++;
+        if (++steps > ROT_BUDGET) { ok = false; break; }
+    }
+    if (!ok || lam > (uint32_t)ROT_LMAX) { mu_out[c] = 0xffffffffu; lambda_out[c] = 0; return; }
+    t_re = 16384; t_im = 0; h_re = 16384; h_im = 0;
+    for (uint32_t i = 0; i < lam; i++) rot_step(h_re, h_im, i_re, i_im);
+    uint32_t mu = 0;
+    while (t_re != h_re || t_im != h_im) {
+        rot_step(t_re, t_im, i_re, i_im);
+        rot_step(h_re, h_im, i_re, i_im);
+        mu++;
+    }
+    for (uint32_t i = 0; i < lam; i++) {
+        cyc[(size_t)c * ROT_LMAX + i] = pack16(t_re, t_im);
+        rot_step(t_re, t_im, i_re, i_im);
+    }
+    mu_out[c] = mu; lambda_out[c] = lam;
+}
+
+/* -------------------------------------------------------------------------------------- */
+/* Per submit: derotator phase at the first FIR output of every tile.
+ * Tile t covers FIR outputs j = 0..KT-1 <-> stream output index g = k0 + t*KP - 1 + j (KP = KT-1);
+ * j = 0 only feeds the discriminator's "previous sample".  ckpt[t][c] = rot at g(t, j = (t==0)). */
+__global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict__ rot_state, int nr_channels,
+                                   const uint32_t *__restrict__ mu, const uint32_t *__restrict__ lambda,
+                                   const int *__restrict__ cyc, unsigned long long k0, unsigned long long K,
+                                   int KP, int nr_tiles, int *__restrict__ ckpt)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nr_channels) return;
+    const int i_re = lo16(incr[c]), i_im = hi16(incr[c]);
+    const uint32_t m = mu[c], lam = lambda[c];
+    const int *tab = cyc + (size_t)c * ROT_LMAX;
+    int r_re = lo16(rot_state[c]), r_im = hi16(rot_state[c]);
+    unsigned long long cur = k0;                 /* (r_re, r_im) == rot at output index cur */
+
+    auto seek = [&](unsigned long long g) {
+        if (lam != 0 && g >= (unsigned long long)m) {
+            const int w = tab[(g - m) % lam];
+            r_re = lo16(w); r_im = hi16(w);
+        } else {
+            while (cur < g) { rot_step(r_re, r_im, i_re, i_im); cur++; }
+        }
+        cur = g;
+    };
+
+    for (int t = 0; t < nr_tiles; t++) {
+        const unsigned long long g = k0 + (unsigned long long)t * KP - (t > 0 ? 1 : 0);
+        seek(g);
+        ckpt[(size_t)t * nr_channels + c] = pack16(r_re, r_im);
+    }
+    seek(k0 + K);
+    rot_state[c] = pack16(r_re, r_im);
+}
+
+/* -------------------------------------------------------------------------------------- */
+struct FirFmParams {
+    InWindow in;
+    const int *taps;        /* [T][Cpad] packed (c_re | c_im << 16) */
+    const int *incr;        /* [C] */
+    const int *ckpt;        /* [tiles][C] */
+    const int *last_in;     /* [C] packed y[k0-1] */
+    int *last_out;          /* [C] */
+    const float2 *atan_tab; /* [256] */
+    short *pcm;             /* [C][pitch] */
+    int *iq_out;            /* [C][pitch] or null */
+    long long pitch;
+    unsigned long long K;   /* outputs of this submit (per channel) */
+    int T, D, C, Cpad;
+    int first_stream;       /* 1 if k0 == 0: y[-1] = 0 comes from last_in (zero) */
+    AtanParams atan;
+};
+
+template <int CPT, int R>
+__global__ void __launch_bounds__(CTA_THREADS, 1) fir_fm_imad_kernel(const FirFmParams p)
+{
+    constexpr int CG = 32 * CPT;            /* channels per CTA */
+    constexpr int KT = FIR_WARPS * R;       /* FIR outputs per tile */
+    constexpr int KP = KT - 1;              /* PCM outputs per tile */
+    constexpr int QP = KT + 1;              /* padded row pitch of qbuf / rotbuf */
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = p.T, D = p.D;
+    const int W = KP * D + T;               /* input samples needed by the tile */
+    int2 *win     = reinterpret_cast<int2 *>(smem_raw);                 /* [W] (a, b) */
+    int *taps_s   = reinterpret_cast<int *>(win + W);                   /* [T][CG] packed */
+    int *qbuf     = taps_s + T * CG;                                    /* [CG][QP] packed q */
+    int *rotbuf   = qbuf + CG * QP;                                     /* [CG][QP] packed rot */
+    float2 *atan_s = reinterpret_cast<float2 *>(rotbuf + CG * QP);      /* [256] */
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    const int c_base = blockIdx.y * CG;
+    /* stream-relative index of FIR output j = 0 of this tile (may be -1 for tile 0) */
+    const long long kf = (long long)tile * KP - 1;
+    const long long s0 = kf * D;
+
+    /* ---- stage: input window (unpacked to int32 pairs), taps, atan table ---- */
+    for (int i = tid; i < W; i += CTA_THREADS) {
+        const int w = in_sample(p.in, s0 + i);
+        win[i] = make_int2(lo16(w), hi16(w));
+    }
+    for (int i = tid; i < T * CG; i += CTA_THREADS) {
+        const int ti = i / CG, ch = i - ti * CG;
+        const int c = c_base + ch;
+        taps_s[i] = (c < p.Cpad) ? __ldg(p.taps + (size_t)ti * p.Cpad + c) : 0;
+    }
+    for (int i = tid; i < 256; i += CTA_THREADS) atan_s[i] = p.atan_tab[i];
+    __syncthreads();
+
+    if (warp < FIR_WARPS) {
+        /* ---- FIR: lane = channel (CPT channels per thread), warp*R.. = R consecutive outputs ---- */
+        int A1[CPT][R], A2[CPT][R], A3[CPT][R];
+#pragma unroll
+        for (int u = 0; u < CPT; u++)
+#pragma unroll
+            for (int r = 0; r < R; r++) { A1[u][r] = 0; A2[u][r] = 0; A3[u][r] = 0; }
+
+        const int2 *wbase = win + (warp * R) * D;
+        const int *tp = taps_s + lane;
+#pragma unroll 2
+        for (int i = 0; i < T; i++) {
+            int tc[CPT], tdmc[CPT], tcpd[CPT];
+#pragma unroll
+            for (int u = 0; u < CPT; u++) {
+                const int tw = tp[i * CG + 32 * u];
+                const int c = lo16(tw), d = hi16(tw);
+                tc[u] = c; tdmc[u] = d - c; tcpd[u] = c + d;
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int2 s = wbase[r * D + i];
+                const int ab = s.x + s.y;
+#pragma unroll
+                for (int u = 0; u < CPT; u++) {
+                    A1[u][r] += tc[u] * ab;
+                    A2[u][r] += s.x * tdmc[u];
+                    A3[u][r] += s.y * tcpd[u];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CPT; u++)
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int re = A1[u][r] - A3[u][r];
+                const int im = A1[u][r] + A2[u][r];
+                qbuf[(lane + 32 * u) * QP + warp * R + r] = pack16(rq14(re), rq14(im));
+            }
+    } else {
+        /* ---- derotator sequence for this tile (sequential per channel) ---- */
+#pragma unroll
+        for (int u = 0; u < CPT; u++) {
+            const int ch = lane + 32 * u, c = c_base + ch;
+            if (c < p.C) {
+                const int iw = __ldg(p.incr + c);
+                const int i_re = lo16(iw), i_im = hi16(iw);
+                const int cw = __ldg(p.ckpt + (size_t)tile * p.C + c);
+                int r_re = lo16(cw), r_im = hi16(cw);
+                const int j0 = (tile == 0) ? 1 : 0;
+                for (int j = j0; j < KT; j++) {
+                    rotbuf[ch * QP + j] = pack16(r_re, r_im);
+                    rot_step(r_re, r_im, i_re, i_im);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    /* ---- epilogue: derotate, discriminate, store; lanes run along time for coalesced stores ---- */
+    const bool derot = true;
+    for (int e = tid; e < CG * KP; e += CTA_THREADS) {
+        const int ch = e / KP, jj = e - ch * KP + 1;
+        const int c = c_base + ch;
+        const long long k = (long long)tile * KP + (jj - 1);
+        if (c >= p.C || (unsigned long long)k >= p.K) continue;
+        const int qw = qbuf[ch * QP + jj], rw = rotbuf[ch * QP + jj];
+        int y_re, y_im, p_re, p_im;
+        if (derot) derotate(lo16(qw), hi16(qw), lo16(rw), hi16(rw), y_re, y_im);
+        if (tile == 0 && jj == 1) {
+            const int lw = __ldg(p.last_in + c);
+            p_re = lo16(lw); p_im = hi16(lw);
+        } else {
+            const int qv = qbuf[ch * QP + jj - 1], rv = rotbuf[ch * QP + jj - 1];
+            derotate(lo16(qv), hi16(qv), lo16(rv), hi16(rv), p_re, p_im);
+        }
+        const int pcm = fm_pcm(y_re, y_im, p_re, p_im, atan_s, p.atan);
+        p.pcm[(size_t)c * p.pitch + k] = (short)pcm;
+        if (p.iq_out) p.iq_out[(size_t)c * p.pitch + k] = pack16(y_re, y_im);
+        if ((unsigned long long)k == p.K - 1) p.last_out[c] = pack16(y_re, y_im);
+    }
+}
+
+__global__ void carry_save_kernel(InWindow in, long long from, int *__restrict__ dst, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = in_sample(in, from + i);
+}
+
+template <int CPT, int R>
+size_t imad_smem_bytes(int T, int D)
+{
+    constexpr int CG = 32 * CPT, KT = FIR_WARPS * R, KP = KT - 1, QP = KT + 1;
+    const size_t W = (size_t)KP * D + T;
+    return W * 8 + (size_t)T * CG * 4 + 2 * (size_t)CG * QP * 4 + 256 * 8;
+}
+
+} // namespace
+
+/* ------------------------------------------------------------------------------------------ */
+/* host object                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+struct gpuchan {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_own = nullptr, ev_ext = nullptr;
+    int T = 0, D = 0, C = 0, Cpad = 0;
+    uint32_t fs = 0, flags = 0;
+    int engine = GPUCHAN_ENGINE_IMAD;
+    size_t max_batch = 0;
+    int smem_max = 0;
+
+    std::vector<int16_t> h_re, h_im;     /* [C][T] */
+    std::vector<int> h_incr;             /* packed */
+
+    int *d_taps = nullptr;               /* [T][Cpad] packed */
+    int *d_incr = nullptr, *d_rot = nullptr;
+    int *d_last[2] = { nullptr, nullptr };
+    uint32_t *d_mu = nullptr, *d_lambda = nullptr;
+    int *d_cyc = nullptr;
+    int *d_carry[2] = { nullptr, nullptr };
+    int *d_stage = nullptr;
+    int *d_ckpt = nullptr;
+    size_t ckpt_tiles = 0;
+    float2 *d_atan = nullptr;
+    int16_t *d_pcm = nullptr;
+    int *d_iq = nullptr;
+    size_t pitch = 0;
+
+    int pp_last = 0, pp_carry = 0;
+    long long carry_len = 0;
+    long long skip = 0;                  /* input samples still to be dropped (only when D > T) */
+    unsigned long long k_total = 0;
+    size_t last_K = 0;
+    uint64_t launches = 0;
+    AtanParams atan{};
+
+    /* kernel variant */
+    int cpt = 2, R = 8;
+};
+
+static void host_atan_table(float2 *out)
+{
+    /* The reference table (multifm/fast_atan2f.c:15-81) holds atan(i/255), i = 0..255, printed with 7
+     * significant digits ("%.6e"), plus one duplicated guard entry; regenerated here bit-identically. */
+    float t[257];
+    for (int i = 0; i < 257; i++) {
+        char txt[32];
+        const int j = i > 255 ? 255 : i;
+        snprintf(txt, sizeof(txt), "%.6e", atan((double)j / 255.0));
+        t[i] = strtof(txt, nullptr);
+    }
+    for (int i = 0; i < 256; i++) out[i] = make_float2(t[i], t[i + 1] - t[i]);
+}
+
+static int free_all(gpuchan *h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_taps); cudaFree(h->d_incr); cudaFree(h->d_rot);
+    cudaFree(h->d_last[0]); cudaFree(h->d_last[1]);
+    cudaFree(h->d_mu); cudaFree(h->d_lambda); cudaFree(h->d_cyc);
+    cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_stage); cudaFree(h->d_ckpt);
+    cudaFree(h->d_atan); cudaFree(h->d_pcm); cudaFree(h->d_iq);
+    if (h->ev_own) cudaEventDestroy(h->ev_own);
+    if (h->ev_ext) cudaEventDestroy(h->ev_ext);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+template <int CPT, int R>
+static bool variant_fits(const gpuchan *h)
+{
+    return imad_smem_bytes<CPT, R>(h->T, h->D) <= (size_t)h->smem_max;
+}
+
+extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
+{
+    if (!ph || !cfg) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    *ph = nullptr;
+    if (cfg->struct_size != sizeof(gpuchan_cfg)) return set_err(GPUCHAN_E_BADARGS, "gpuchan_cfg size mismatch");
+    if (!cfg->sample_rate_hz || !cfg->decimation || cfg->nr_taps < 2 || !cfg->nr_channels || !cfg->lpf_taps ||
+        !cfg->offset_hz || !cfg->max_batch_samples)
+        return set_err(GPUCHAN_E_BADARGS, "incomplete configuration");
+    if (cfg->decimation > cfg->nr_taps)
+        return set_err(GPUCHAN_E_INVAL, "decimation > nr_taps is undefined in the reference (direct_fir.c:394-401)");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(GPUCHAN_E_NODEVICE, "no CUDA device: this library has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return set_err(GPUCHAN_E_BADARGS, "bad device ordinal %d", cfg->device);
+    cudaDeviceProp prop{};
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return set_err(GPUCHAN_E_NODEVICE, "device %d is sm_%d%d; this build is sm_100a only", cfg->device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+
+    gpuchan *h = new (std::nothrow) gpuchan();
+    if (!h) return set_err(GPUCHAN_E_NOMEM, "out of memory");
+    h->device = cfg->device;
+    h->T = (int)cfg->nr_taps; h->D = (int)cfg->decimation; h->C = (int)cfg->nr_channels;
+    h->Cpad = (h->C + 63) & ~63;
+    h->fs = cfg->sample_rate_hz; h->flags = cfg->flags; h->max_batch = cfg->max_batch_samples;
+    h->smem_max = (int)prop.sharedMemPerBlockOptin;
+    h->engine = GPUCHAN_ENGINE_IMAD;
+
+#define FAIL_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            set_err(GPUCHAN_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            free_all(h);                                                                        \
+            return GPUCHAN_E_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+    FAIL_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    FAIL_TRY(cudaEventCreateWithFlags(&h->ev_own, cudaEventDisableTiming));
+    FAIL_TRY(cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming));
+
+    /* --- a1: taps and derotator increments on the host --- */
+    const int T = h->T, C = h->C, Cpad = h->Cpad;
+    h->h_re.resize((size_t)C * T); h->h_im.resize((size_t)C * T); h->h_incr.resize(C);
+    std::vector<int> packed((size_t)T * Cpad, 0);
+    for (int c = 0; c < C; c++) {
+        const double g = cfg->gain ? cfg->gain[c] : 1.0;
+        gpuchan_prepare_taps(cfg->lpf_taps, T, cfg->offset_hz[c], h->fs, g, &h->h_re[(size_t)c * T], &h->h_im[(size_t)c * T]);
+        int16_t inc[2];
+        gpuchan_derot_increment(cfg->offset_hz[c], h->fs, h->D, inc);
+        h->h_incr[c] = ((int)inc[0] & 0xffff) | ((int)inc[1] << 16);
+        for (int i = 0; i < T; i++)
+            packed[(size_t)i * Cpad + c] = ((int)h->h_re[(size_t)c * T + i] & 0xffff) | ((int)h->h_im[(size_t)c * T + i] << 16);
+    }
+
+    /* --- pick the kernel variant that fits shared memory --- */
+    if      (C > 32 && variant_fits<2, 8>(h)) { h->cpt = 2; h->R = 8; }
+    else if (variant_fits<1, 8>(h) && C <= 32) { h->cpt = 1; h->R = 8; }
+    else if (C > 32 && variant_fits<2, 4>(h)) { h->cpt = 2; h->R = 4; }
+    else if (variant_fits<1, 8>(h))           { h->cpt = 1; h->R = 8; }
+    else if (variant_fits<1, 4>(h))           { h->cpt = 1; h->R = 4; }
+    else { free_all(h); return set_err(GPUCHAN_E_INVAL, "taps=%d decimation=%d do not fit shared memory", T, h->D); }
+
+    const int KP = FIR_WARPS * h->R - 1;
+    const size_t max_avail = h->max_batch + (size_t)T;
+    const size_t max_K = max_avail / h->D + 2;
+    h->pitch = (max_K + 63) & ~(size_t)63;
+    h->ckpt_tiles = (max_K + KP - 1) / KP + 1;
+
+    FAIL_TRY(cudaMalloc(&h->d_taps, packed.size() * sizeof(int)));
+    FAIL_TRY(cudaMemcpy(h->d_taps, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice));
+    FAIL_TRY(cudaMalloc(&h->d_incr, C * sizeof(int)));
+    FAIL_TRY(cudaMemcpy(h->d_incr, h->h_incr.data(), C * sizeof(int), cudaMemcpyHostToDevice));
+    std::vector<int> rot0(C, 16384);             /* direct_fir.c:78-79: rot = (1<<14, 0) */
+    FAIL_TRY(cudaMalloc(&h->d_rot, C * sizeof(int)));
+    FAIL_TRY(cudaMemcpy(h->d_rot, rot0.data(), C * sizeof(int), cudaMemcpyHostToDevice));
+    for (int i = 0; i < 2; i++) {
+        FAIL_TRY(cudaMalloc(&h->d_last[i], C * sizeof(int)));
+        FAIL_TRY(cudaMemset(h->d_last[i], 0, C * sizeof(int)));     /* fm_demod.c: last sample starts at 0 */
+        FAIL_TRY(cudaMalloc(&h->d_carry[i], (size_t)(T + 1) * sizeof(int)));
+    }
+    FAIL_TRY(cudaMalloc(&h->d_mu, C * sizeof(uint32_t)));
+    FAIL_TRY(cudaMalloc(&h->d_lambda, C * sizeof(uint32_t)));
+    FAIL_TRY(cudaMalloc(&h->d_cyc, (size_t)C * ROT_LMAX * sizeof(int)));
+    FAIL_TRY(cudaMalloc(&h->d_stage, h->max_batch * sizeof(int)));
+    FAIL_TRY(cudaMalloc(&h->d_ckpt, h->ckpt_tiles * C * sizeof(int)));
+    FAIL_TRY(cudaMalloc(&h->d_pcm, (size_t)C * h->pitch * sizeof(int16_t)));
+    if (h->flags & GPUCHAN_F_KEEP_IQ) FAIL_TRY(cudaMalloc(&h->d_iq, (size_t)C * h->pitch * sizeof(int)));
+    float2 tab[256];
+    host_atan_table(tab);
+    FAIL_TRY(cudaMalloc(&h->d_atan, sizeof(tab)));
+    FAIL_TRY(cudaMemcpy(h->d_atan, tab, sizeof(tab), cudaMemcpyHostToDevice));
+
+    /* (double)z < 0.003921569 as a float comparison (fast_atan2f.c:123) */
+    {
+        const double res = 0.003921569;
+        float f = (float)res;
+        if ((double)f < res) f = nextafterf(f, INFINITY);
+        h->atan.z_small_thr = f;
+        h->atan.use_fma = (h->flags & GPUCHAN_F_ATAN_FMA) ? 1 : 0;
+    }
+
+    /* --- derotator limit cycles --- */
+    rot_cycle_detect_kernel<<<(C + 63) / 64, 64, 0, h->stream>>>(h->d_incr, C, h->d_mu, h->d_lambda, h->d_cyc);
+    h->launches++;
+    FAIL_TRY(cudaGetLastError());
+    FAIL_TRY(cudaStreamSynchronize(h->stream));
+#undef FAIL_TRY
+    *ph = h;
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_destroy(gpuchan_t **ph)
+{
+    if (!ph || !*ph) return set_err(GPUCHAN_E_BADARGS, "null handle");
+    cudaSetDevice((*ph)->device);
+    cudaStreamSynchronize((*ph)->stream);
+    free_all(*ph);
+    *ph = nullptr;
+    return GPUCHAN_OK;
+}
+
+template <int CPT, int R>
+static cudaError_t launch_imad(gpuchan *h, const FirFmParams &p, int nr_tiles, cudaStream_t st)
+{
+    const size_t smem = imad_smem_bytes<CPT, R>(h->T, h->D);
+    static thread_local int configured_for = -1;
+    (void)configured_for;
+    cudaError_t e = cudaFuncSetAttribute(fir_fm_imad_kernel<CPT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(nr_tiles, (h->C + 32 * CPT - 1) / (32 * CPT));
+    fir_fm_imad_kernel<CPT, R><<<grid, CTA_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+extern "C" int gpuchan_submit_device(gpuchan_t *h, const int16_t *d_iq, size_t n_complex, void *cuda_stream)
+{
+    if (!h || (!d_iq && n_complex)) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    if (n_complex > h->max_batch) return set_err(GPUCHAN_E_INVAL, "submit of %zu samples exceeds max_batch_samples %zu", n_complex, h->max_batch);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (st != h->stream) {      /* order the caller's stream after everything already queued on ours */
+        CUDA_TRY(cudaEventRecord(h->ev_own, h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_own, 0));
+    }
+
+    const long long avail = h->carry_len + (long long)n_complex;
+    const int T = h->T, D = h->D;
+    const unsigned long long K = (avail >= T) ? (unsigned long long)((avail - T) / D + 1) : 0;
+
+    InWindow in;
+    in.carry = h->d_carry[h->pp_carry];
+    in.fresh = reinterpret_cast<const int *>(d_iq);
+    in.carry_len = h->carry_len;
+    in.total = avail;
+
+    if (K > 0) {
+        const int KP = FIR_WARPS * h->R - 1;
+        const int nr_tiles = (int)((K + KP - 1) / KP);
+        if ((size_t)nr_tiles > h->ckpt_tiles || K > h->pitch) return set_err(GPUCHAN_E_INVAL, "internal capacity exceeded");
+
+        rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, st>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
+                                                            h->k_total, K, KP, nr_tiles, h->d_ckpt);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+
+        FirFmParams p;
+        p.in = in;
+        p.taps = h->d_taps; p.incr = h->d_incr; p.ckpt = h->d_ckpt;
+        p.last_in = h->d_last[h->pp_last]; p.last_out = h->d_last[h->pp_last ^ 1];
+        p.atan_tab = h->d_atan;
+        p.pcm = h->d_pcm; p.iq_out = h->d_iq; p.pitch = (long long)h->pitch;
+        p.K = K; p.T = T; p.D = D; p.C = h->C; p.Cpad = h->Cpad;
+        p.first_stream = (h->k_total == 0);
+        p.atan = h->atan;
+
+        cudaError_t e;
+        if      (h->cpt == 2 && h->R == 8) e = launch_imad<2, 8>(h, p, nr_tiles, st);
+        else if (h->cpt == 2 && h->R == 4) e = launch_imad<2, 4>(h, p, nr_tiles, st);
+        else if (h->cpt == 1 && h->R == 8) e = launch_imad<1, 8>(h, p, nr_tiles, st);
+        else                               e = launch_imad<1, 4>(h, p, nr_tiles, st);
+        h->launches++;
+        CUDA_TRY(e);
+        h->pp_last ^= 1;
+        h->k_total += K;
+    }
+
+    /* keep what the next submit still needs: samples [K*D, avail) */
+    const long long from = (long long)K * D;
+    const long long keep = avail - from;     /* < T */
+    if (keep > 0) {
+        carry_save_kernel<<<(unsigned)((keep + 255) / 256), 256, 0, st>>>(in, from, h->d_carry[h->pp_carry ^ 1], (int)keep);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    h->pp_carry ^= 1;
+    h->carry_len = keep > 0 ? keep : 0;
+    h->last_K = (size_t)K;
+    if (st != h->stream) {      /* ... and our stream (collect, next host submit) after the caller's */
+        CUDA_TRY(cudaEventRecord(h->ev_ext, st));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_ext, 0));
+    }
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_submit(gpuchan_t *h, const int16_t *iq_host, size_t n_complex)
+{
+    if (!h || (!iq_host && n_complex)) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    if (n_complex > h->max_batch) return set_err(GPUCHAN_E_INVAL, "submit of %zu samples exceeds max_batch_samples %zu", n_complex, h->max_batch);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (n_complex) CUDA_TRY(cudaMemcpyAsync(h->d_stage, iq_host, n_complex * 4, cudaMemcpyHostToDevice, h->stream));
+    return gpuchan_submit_device(h, reinterpret_cast<const int16_t *>(h->d_stage), n_complex, nullptr);
+}
+
+extern "C" int gpuchan_sync(gpuchan_t *h)
+{
+    if (!h) return set_err(GPUCHAN_E_BADARGS, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_pending(gpuchan_t *h, size_t *n)
+{
+    if (!h || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    *n = h->last_K;
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_collect(gpuchan_t *h, int16_t *pcm_host, size_t cap, size_t *n)
+{
+    if (!h || !pcm_host || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    *n = h->last_K;
+    if (h->last_K > cap) return set_err(GPUCHAN_E_INVAL, "collect capacity %zu < %zu outputs", cap, h->last_K);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->last_K)
+        CUDA_TRY(cudaMemcpy2DAsync(pcm_host, cap * sizeof(int16_t), h->d_pcm, h->pitch * sizeof(int16_t),
+                                   h->last_K * sizeof(int16_t), h->C, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_collect_iq(gpuchan_t *h, int16_t *iq_host, size_t cap, size_t *n)
+{
+    if (!h || !iq_host || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    if (!h->d_iq) return set_err(GPUCHAN_E_INVAL, "bank was created without GPUCHAN_F_KEEP_IQ");
+    *n = h->last_K;
+    if (h->last_K > cap) return set_err(GPUCHAN_E_INVAL, "collect capacity %zu < %zu outputs", cap, h->last_K);
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->last_K)
+        CUDA_TRY(cudaMemcpy2DAsync(iq_host, cap * 4, h->d_iq, h->pitch * 4, h->last_K * 4, h->C,
+                                   cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_device_pcm(gpuchan_t *h, const int16_t **d_pcm, size_t *pitch, size_t *n)
+{
+    if (!h || !d_pcm || !pitch || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    *d_pcm = h->d_pcm; *pitch = h->pitch; *n = h->last_K;
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_get_taps(gpuchan_t *h, uint32_t channel, int16_t *c_re, int16_t *c_im)
+{
+    if (!h || !c_re || !c_im || channel >= (uint32_t)h->C) return set_err(GPUCHAN_E_BADARGS, "bad argument");
+    memcpy(c_re, &h->h_re[(size_t)channel * h->T], h->T * sizeof(int16_t));
+    memcpy(c_im, &h->h_im[(size_t)channel * h->T], h->T * sizeof(int16_t));
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_get_rot_state(gpuchan_t *h, uint32_t channel, int16_t rot[2], int16_t incr[2],
+                                     uint64_t *outputs_so_far, uint32_t *cycle_mu, uint32_t *cycle_lambda)
+{
+    if (!h || channel >= (uint32_t)h->C) return set_err(GPUCHAN_E_BADARGS, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int w = 0;
+    uint32_t mu = 0, lam = 0;
+    CUDA_TRY(cudaMemcpy(&w, h->d_rot + channel, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&mu, h->d_mu + channel, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&lam, h->d_lambda + channel, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (rot) { rot[0] = (int16_t)(w & 0xffff); rot[1] = (int16_t)(w >> 16); }
+    if (incr) { incr[0] = (int16_t)(h->h_incr[channel] & 0xffff); incr[1] = (int16_t)(h->h_incr[channel] >> 16); }
+    if (outputs_so_far) *outputs_so_far = h->k_total;
+    if (cycle_mu) *cycle_mu = mu;
+    if (cycle_lambda) *cycle_lambda = lam;
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_engine(gpuchan_t *h) { return h ? h->engine : GPUCHAN_E_BADARGS; }
+extern "C" uint64_t gpuchan_kernel_launches(gpuchan_t *h) { return h ? h->launches : 0; }

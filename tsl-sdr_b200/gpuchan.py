@@ -1,0 +1,157 @@
+"""ctypes mirror of include/tslb200_gpuchan.h (host-side view of the channel bank)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+F_ATAN_FMA = 0x1
+F_KEEP_IQ = 0x2
+ENGINE_AUTO, ENGINE_IMAD, ENGINE_TC = 0, 1, 2
+
+
+class GpuChanError(RuntimeError):
+    def __init__(self, code, where):
+        msg = _lib.lib().gpuchan_last_error()
+        super().__init__(f"{where} failed: {code} ({msg.decode() if msg else ''})")
+        self.code = code
+
+
+def _check(code, where):
+    if code != 0:
+        raise GpuChanError(code, where)
+
+
+def prepare_taps(lpf, offset_hz, fs, gain=1.0):
+    lpf = np.ascontiguousarray(lpf, dtype=np.float64)
+    re = np.zeros(len(lpf), np.int16)
+    im = np.zeros(len(lpf), np.int16)
+    _check(_lib.lib().gpuchan_prepare_taps(lpf.ctypes.data, len(lpf), int(offset_hz), int(fs), float(gain),
+                                           re.ctypes.data, im.ctypes.data), "gpuchan_prepare_taps")
+    return re, im
+
+
+def derot_increment(offset_hz, fs, decimation):
+    out = np.zeros(2, np.int16)
+    _check(_lib.lib().gpuchan_derot_increment(int(offset_hz), int(fs), int(decimation), out.ctypes.data),
+           "gpuchan_derot_increment")
+    return out
+
+
+def db_to_gain(db):
+    return _lib.lib().gpuchan_db_to_gain(float(db))
+
+
+class GpuChan:
+    """One bank = all channels of a receiver on one GPU (replaces N demod threads)."""
+
+    def __init__(self, lpf_taps, offsets_hz, sample_rate_hz, decimation, max_batch_samples, device=0,
+                 gains=None, flags=F_ATAN_FMA, engine=ENGINE_AUTO):
+        L = _lib.lib()
+        self._L = L
+        self._lpf = np.ascontiguousarray(lpf_taps, dtype=np.float64)
+        self._offs = np.ascontiguousarray(offsets_hz, dtype=np.int32)
+        self._gains = None if gains is None else np.ascontiguousarray(gains, dtype=np.float64)
+        cfg = _lib.GpuChanCfg()
+        cfg.struct_size = C.sizeof(_lib.GpuChanCfg)
+        cfg.sample_rate_hz = int(sample_rate_hz)
+        cfg.decimation = int(decimation)
+        cfg.nr_taps = len(self._lpf)
+        cfg.nr_channels = len(self._offs)
+        cfg.device = int(device)
+        cfg.max_batch_samples = int(max_batch_samples)
+        cfg.flags = int(flags)
+        cfg.engine = int(engine)
+        cfg.lpf_taps = self._lpf.ctypes.data_as(C.POINTER(C.c_double))
+        cfg.offset_hz = self._offs.ctypes.data_as(C.POINTER(C.c_int32))
+        cfg.gain = self._gains.ctypes.data_as(C.POINTER(C.c_double)) if self._gains is not None else None
+        self._h = C.c_void_p()
+        _check(L.gpuchan_create(C.byref(self._h), C.byref(cfg)), "gpuchan_create")
+        self.nr_channels = len(self._offs)
+        self.nr_taps = len(self._lpf)
+        self.decimation = int(decimation)
+        self.flags = int(flags)
+        self.max_batch = int(max_batch_samples)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.gpuchan_destroy(C.byref(self._h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- data path ----------------------------------------------------------------------
+    def submit(self, iq_host: np.ndarray):
+        """iq_host: interleaved int16 I,Q in host memory."""
+        assert iq_host.dtype == np.int16 and iq_host.flags.c_contiguous
+        _check(self._L.gpuchan_submit(self._h, iq_host.ctypes.data, len(iq_host) // 2), "gpuchan_submit")
+
+    def submit_ptr(self, host_ptr: int, n_complex: int):
+        _check(self._L.gpuchan_submit(self._h, host_ptr, n_complex), "gpuchan_submit")
+
+    def submit_device(self, dev_ptr: int, n_complex: int, stream: int = 0):
+        _check(self._L.gpuchan_submit_device(self._h, dev_ptr, n_complex, stream), "gpuchan_submit_device")
+
+    def sync(self):
+        _check(self._L.gpuchan_sync(self._h), "gpuchan_sync")
+
+    def pending(self) -> int:
+        n = C.c_size_t(0)
+        _check(self._L.gpuchan_pending(self._h, C.byref(n)), "gpuchan_pending")
+        return n.value
+
+    def collect(self, out: np.ndarray | None = None) -> np.ndarray:
+        """PCM of the last submit as [nr_channels, n] int16."""
+        k = self.pending()
+        if out is None:
+            out = np.zeros((self.nr_channels, max(k, 1)), np.int16)
+        n = C.c_size_t(0)
+        _check(self._L.gpuchan_collect(self._h, out.ctypes.data, out.shape[1], C.byref(n)), "gpuchan_collect")
+        return out[:, :n.value]
+
+    def collect_into(self, host_ptr: int, cap_per_channel: int) -> int:
+        n = C.c_size_t(0)
+        _check(self._L.gpuchan_collect(self._h, host_ptr, cap_per_channel, C.byref(n)), "gpuchan_collect")
+        return n.value
+
+    def collect_iq(self) -> np.ndarray:
+        k = self.pending()
+        out = np.zeros((self.nr_channels, max(k, 1), 2), np.int16)
+        n = C.c_size_t(0)
+        _check(self._L.gpuchan_collect_iq(self._h, out.ctypes.data, out.shape[1], C.byref(n)), "gpuchan_collect_iq")
+        return out[:, :n.value, :]
+
+    def device_pcm(self):
+        p, pitch, n = C.c_void_p(), C.c_size_t(0), C.c_size_t(0)
+        _check(self._L.gpuchan_device_pcm(self._h, C.byref(p), C.byref(pitch), C.byref(n)), "gpuchan_device_pcm")
+        return p.value, pitch.value, n.value
+
+    # -- introspection ---------------------------------------------------------------------
+    def taps(self, channel):
+        re = np.zeros(self.nr_taps, np.int16)
+        im = np.zeros(self.nr_taps, np.int16)
+        _check(self._L.gpuchan_get_taps(self._h, channel, re.ctypes.data, im.ctypes.data), "gpuchan_get_taps")
+        return re, im
+
+    def rot_state(self, channel):
+        rot = np.zeros(2, np.int16)
+        incr = np.zeros(2, np.int16)
+        k = C.c_uint64(0)
+        mu = C.c_uint32(0)
+        lam = C.c_uint32(0)
+        _check(self._L.gpuchan_get_rot_state(self._h, channel, rot.ctypes.data, incr.ctypes.data, C.byref(k),
+                                             C.byref(mu), C.byref(lam)), "gpuchan_get_rot_state")
+        return rot, incr, k.value, mu.value, lam.value
+
+    @property
+    def engine(self):
+        return self._L.gpuchan_engine(self._h)
+
+    @property
+    def kernel_launches(self):
+        return self._L.gpuchan_kernel_launches(self._h)
