@@ -91,17 +91,25 @@ int gpuchan_submit_device(gpuchan_t *h, const int16_t *d_iq, size_t n_complex, v
 /* Wait for all submitted work. */
 int gpuchan_sync(gpuchan_t *h);
 
-/* Number of PCM samples per channel produced by the LAST submit (identical for all channels). */
+/* Up to two submits may be in flight (the H2D copy of batch i overlaps the kernels of batch i-1 and the D2H
+ * of batch i-2); a third submit returns GPUCHAN_E_BUSY until the oldest batch is collected or discarded.
+ * Results come back in FIFO order. */
+int gpuchan_in_flight(gpuchan_t *h);
+
+/* Number of PCM samples per channel in the OLDEST uncollected batch (identical for all channels; 0 if none). */
 int gpuchan_pending(gpuchan_t *h, size_t *n_per_channel);
 
-/* Copy the last submit's PCM to host: channel c occupies pcm_host[c*cap_per_channel ... + n).
- * Blocks until the data has arrived. */
+/* Copy the oldest uncollected batch's PCM to host: channel c occupies pcm_host[c*cap_per_channel ... + n).
+ * Blocks until the data has arrived, then retires the batch. */
 int gpuchan_collect(gpuchan_t *h, int16_t *pcm_host, size_t cap_per_channel, size_t *n_per_channel);
-/* Same for the post-FIR IQ tap (2 int16 per output); needs GPUCHAN_F_KEEP_IQ. */
+/* Post-FIR IQ tap (2 int16 per output) of the batch most recently returned by gpuchan_collect;
+ * needs GPUCHAN_F_KEEP_IQ and must be called before that batch's slot is reused (two submits later). */
 int gpuchan_collect_iq(gpuchan_t *h, int16_t *iq_host, size_t cap_per_channel, size_t *n_per_channel);
+/* Retire the oldest batch without copying it (results consumed on the device, or not wanted). */
+int gpuchan_discard(gpuchan_t *h);
 
-/* Device view of the last submit's PCM for chaining on-GPU consumers (pager bank): channel c starts at
- * d_pcm + c * pitch_samples. Valid until the next submit. */
+/* Device view of the MOST RECENT submit's PCM for chaining on-GPU consumers (pager bank): channel c starts at
+ * d_pcm + c * pitch_samples. Valid until that slot is reused (two submits later). */
 int gpuchan_device_pcm(gpuchan_t *h, const int16_t **d_pcm, size_t *pitch_samples, size_t *n_per_channel);
 
 /* Introspection for parity tests */
@@ -111,6 +119,10 @@ int gpuchan_get_rot_state(gpuchan_t *h, uint32_t channel, int16_t rot[2], int16_
 int gpuchan_engine(gpuchan_t *h);           /* engine actually in use */
 uint64_t gpuchan_kernel_launches(gpuchan_t *h);  /* kernels launched by this bank so far */
 const char *gpuchan_last_error(void);
+
+/* Instrumentation (bench.py roofline): CUDA events around each launch of the dominant FIR+FM kernel. */
+int gpuchan_timing_enable(gpuchan_t *h, int on);
+int gpuchan_timing_read(gpuchan_t *h, double *total_ms, uint64_t *nr_launches);
 
 #ifdef __cplusplus
 }

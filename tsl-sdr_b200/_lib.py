@@ -55,10 +55,15 @@ def _declare(L: C.CDLL) -> None:
     L.gpuchan_kernel_launches.restype = C.c_uint64
     L.gpuchan_kernel_launches.argtypes = [vp]
     L.gpuchan_last_error.restype = C.c_char_p
+    L.gpuchan_in_flight.argtypes = [vp]
+    L.gpuchan_discard.argtypes = [vp]
+    L.gpuchan_timing_enable.argtypes = [vp, C.c_int]
+    L.gpuchan_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
 
 
 # every symbol include/tslb200_gpuchan.h declares (checked by the CPU test-suite)
 EXPORTS = ["gpuchan_prepare_taps", "gpuchan_derot_increment", "gpuchan_db_to_gain", "gpuchan_create",
            "gpuchan_destroy", "gpuchan_submit", "gpuchan_submit_device", "gpuchan_sync", "gpuchan_pending",
            "gpuchan_collect", "gpuchan_collect_iq", "gpuchan_device_pcm", "gpuchan_get_taps",
-           "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error"]
+           "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error", "gpuchan_timing_enable", "gpuchan_in_flight", "gpuchan_discard",
+           "gpuchan_timing_read"]

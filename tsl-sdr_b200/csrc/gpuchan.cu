@@ -368,21 +368,28 @@ struct gpuchan {
     uint32_t *d_mu = nullptr, *d_lambda = nullptr;
     int *d_cyc = nullptr;
     int *d_carry[2] = { nullptr, nullptr };
-    int *d_stage = nullptr;
+    static constexpr int NSLOT = 2;          /* batches in flight: H2D | kernels | D2H overlap */
+    int *d_stage[NSLOT] = { nullptr, nullptr };
     int *d_ckpt = nullptr;
     size_t ckpt_tiles = 0;
     float2 *d_atan = nullptr;
-    int16_t *d_pcm = nullptr;
-    int *d_iq = nullptr;
+    int16_t *d_pcm[NSLOT] = { nullptr, nullptr };
+    int *d_iq[NSLOT] = { nullptr, nullptr };
+    size_t slotK[NSLOT] = { 0, 0 };
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_h2d[NSLOT] = { nullptr, nullptr }, ev_done[NSLOT] = { nullptr, nullptr };
+    uint64_t submit_seq = 0, collect_seq = 0;
+    int last_slot = -1, collected_slot = -1;
     size_t pitch = 0;
 
     int pp_last = 0, pp_carry = 0;
     long long carry_len = 0;
     long long skip = 0;                  /* input samples still to be dropped (only when D > T) */
     unsigned long long k_total = 0;
-    size_t last_K = 0;
     uint64_t launches = 0;
     AtanParams atan{};
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;   /* around each dominant-kernel launch */
 
     /* kernel variant */
     int cpt = 2, R = 8;
@@ -409,8 +416,15 @@ static int free_all(gpuchan *h)
     cudaFree(h->d_taps); cudaFree(h->d_incr); cudaFree(h->d_rot);
     cudaFree(h->d_last[0]); cudaFree(h->d_last[1]);
     cudaFree(h->d_mu); cudaFree(h->d_lambda); cudaFree(h->d_cyc);
-    cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_stage); cudaFree(h->d_ckpt);
-    cudaFree(h->d_atan); cudaFree(h->d_pcm); cudaFree(h->d_iq);
+    cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_ckpt);
+    cudaFree(h->d_atan);
+    for (int i = 0; i < gpuchan::NSLOT; i++) {
+        cudaFree(h->d_stage[i]); cudaFree(h->d_pcm[i]); cudaFree(h->d_iq[i]);
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->ev_own) cudaEventDestroy(h->ev_own);
     if (h->ev_ext) cudaEventDestroy(h->ev_ext);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -511,10 +525,16 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
     FAIL_TRY(cudaMalloc(&h->d_mu, C * sizeof(uint32_t)));
     FAIL_TRY(cudaMalloc(&h->d_lambda, C * sizeof(uint32_t)));
     FAIL_TRY(cudaMalloc(&h->d_cyc, (size_t)C * ROT_LMAX * sizeof(int)));
-    FAIL_TRY(cudaMalloc(&h->d_stage, h->max_batch * sizeof(int)));
     FAIL_TRY(cudaMalloc(&h->d_ckpt, h->ckpt_tiles * C * sizeof(int)));
-    FAIL_TRY(cudaMalloc(&h->d_pcm, (size_t)C * h->pitch * sizeof(int16_t)));
-    if (h->flags & GPUCHAN_F_KEEP_IQ) FAIL_TRY(cudaMalloc(&h->d_iq, (size_t)C * h->pitch * sizeof(int)));
+    FAIL_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    FAIL_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < gpuchan::NSLOT; i++) {
+        FAIL_TRY(cudaMalloc(&h->d_stage[i], h->max_batch * sizeof(int)));
+        FAIL_TRY(cudaMalloc(&h->d_pcm[i], (size_t)C * h->pitch * sizeof(int16_t)));
+        if (h->flags & GPUCHAN_F_KEEP_IQ) FAIL_TRY(cudaMalloc(&h->d_iq[i], (size_t)C * h->pitch * sizeof(int)));
+        FAIL_TRY(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+        FAIL_TRY(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
     float2 tab[256];
     host_atan_table(tab);
     FAIL_TRY(cudaMalloc(&h->d_atan, sizeof(tab)));
@@ -562,24 +582,23 @@ static cudaError_t launch_imad(gpuchan *h, const FirFmParams &p, int nr_tiles, c
     return cudaGetLastError();
 }
 
-extern "C" int gpuchan_submit_device(gpuchan_t *h, const int16_t *d_iq, size_t n_complex, void *cuda_stream)
+static int slot_acquire(gpuchan *h)
 {
-    if (!h || (!d_iq && n_complex)) return set_err(GPUCHAN_E_BADARGS, "null argument");
-    if (n_complex > h->max_batch) return set_err(GPUCHAN_E_INVAL, "submit of %zu samples exceeds max_batch_samples %zu", n_complex, h->max_batch);
-    CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-    if (st != h->stream) {      /* order the caller's stream after everything already queued on ours */
-        CUDA_TRY(cudaEventRecord(h->ev_own, h->stream));
-        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_own, 0));
-    }
+    if (h->submit_seq - h->collect_seq >= (uint64_t)gpuchan::NSLOT)
+        return set_err(GPUCHAN_E_BUSY, "%d batches in flight: gpuchan_collect() or gpuchan_discard() first", gpuchan::NSLOT);
+    return GPUCHAN_OK;
+}
 
+/* enqueue all kernels of one submit on stream st; outputs land in slot */
+static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStream_t st, int slot)
+{
     const long long avail = h->carry_len + (long long)n_complex;
     const int T = h->T, D = h->D;
     const unsigned long long K = (avail >= T) ? (unsigned long long)((avail - T) / D + 1) : 0;
 
     InWindow in;
     in.carry = h->d_carry[h->pp_carry];
-    in.fresh = reinterpret_cast<const int *>(d_iq);
+    in.fresh = d_fresh;
     in.carry_len = h->carry_len;
     in.total = avail;
 
@@ -598,11 +617,16 @@ extern "C" int gpuchan_submit_device(gpuchan_t *h, const int16_t *d_iq, size_t n
         p.taps = h->d_taps; p.incr = h->d_incr; p.ckpt = h->d_ckpt;
         p.last_in = h->d_last[h->pp_last]; p.last_out = h->d_last[h->pp_last ^ 1];
         p.atan_tab = h->d_atan;
-        p.pcm = h->d_pcm; p.iq_out = h->d_iq; p.pitch = (long long)h->pitch;
+        p.pcm = h->d_pcm[slot]; p.iq_out = h->d_iq[slot]; p.pitch = (long long)h->pitch;
         p.K = K; p.T = T; p.D = D; p.C = h->C; p.Cpad = h->Cpad;
         p.first_stream = (h->k_total == 0);
         p.atan = h->atan;
 
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (h->timing) {
+            CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
+            CUDA_TRY(cudaEventRecord(t0, st));
+        }
         cudaError_t e;
         if      (h->cpt == 2 && h->R == 8) e = launch_imad<2, 8>(h, p, nr_tiles, st);
         else if (h->cpt == 2 && h->R == 4) e = launch_imad<2, 4>(h, p, nr_tiles, st);
@@ -610,6 +634,7 @@ extern "C" int gpuchan_submit_device(gpuchan_t *h, const int16_t *d_iq, size_t n
         else                               e = launch_imad<1, 4>(h, p, nr_tiles, st);
         h->launches++;
         CUDA_TRY(e);
+        if (h->timing) { CUDA_TRY(cudaEventRecord(t1, st)); h->timed.emplace_back(t0, t1); }
         h->pp_last ^= 1;
         h->k_total += K;
     }
@@ -624,8 +649,27 @@ extern "C" int gpuchan_submit_device(gpuchan_t *h, const int16_t *d_iq, size_t n
     }
     h->pp_carry ^= 1;
     h->carry_len = keep > 0 ? keep : 0;
-    h->last_K = (size_t)K;
-    if (st != h->stream) {      /* ... and our stream (collect, next host submit) after the caller's */
+    h->slotK[slot] = (size_t)K;
+    h->last_slot = slot;
+    CUDA_TRY(cudaEventRecord(h->ev_done[slot], st));
+    h->submit_seq++;
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_submit_device(gpuchan_t *h, const int16_t *d_iq, size_t n_complex, void *cuda_stream)
+{
+    if (!h || (!d_iq && n_complex)) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    if (n_complex > h->max_batch) return set_err(GPUCHAN_E_INVAL, "submit of %zu samples exceeds max_batch_samples %zu", n_complex, h->max_batch);
+    if (int rc = slot_acquire(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (st != h->stream) {      /* order the caller's stream after everything already queued on ours */
+        CUDA_TRY(cudaEventRecord(h->ev_own, h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_own, 0));
+    }
+    const int slot = (int)(h->submit_seq % gpuchan::NSLOT);
+    if (int rc = run_batch(h, reinterpret_cast<const int *>(d_iq), n_complex, st, slot)) return rc;
+    if (st != h->stream) {      /* ... and our stream (next host submit) after the caller's */
         CUDA_TRY(cudaEventRecord(h->ev_ext, st));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_ext, 0));
     }
@@ -636,57 +680,92 @@ extern "C" int gpuchan_submit(gpuchan_t *h, const int16_t *iq_host, size_t n_com
 {
     if (!h || (!iq_host && n_complex)) return set_err(GPUCHAN_E_BADARGS, "null argument");
     if (n_complex > h->max_batch) return set_err(GPUCHAN_E_INVAL, "submit of %zu samples exceeds max_batch_samples %zu", n_complex, h->max_batch);
+    if (int rc = slot_acquire(h)) return rc;
     CUDA_TRY(cudaSetDevice(h->device));
-    if (n_complex) CUDA_TRY(cudaMemcpyAsync(h->d_stage, iq_host, n_complex * 4, cudaMemcpyHostToDevice, h->stream));
-    return gpuchan_submit_device(h, reinterpret_cast<const int16_t *>(h->d_stage), n_complex, nullptr);
+    const int slot = (int)(h->submit_seq % gpuchan::NSLOT);
+    /* copy engine: H2D of batch i overlaps the kernels of batch i-1 and the D2H of batch i-2.
+     * The staging slot was last read by the kernels of batch i-2 (ev_done of this slot). */
+    CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));
+    if (n_complex) CUDA_TRY(cudaMemcpyAsync(h->d_stage[slot], iq_host, n_complex * 4, cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
+    return run_batch(h, h->d_stage[slot], n_complex, h->stream, slot);
 }
 
 extern "C" int gpuchan_sync(gpuchan_t *h)
 {
     if (!h) return set_err(GPUCHAN_E_BADARGS, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
+    for (int i = 0; i < gpuchan::NSLOT; i++) CUDA_TRY(cudaEventSynchronize(h->ev_done[i]));
+    CUDA_TRY(cudaStreamSynchronize(h->s_in));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->s_out));
     return GPUCHAN_OK;
 }
 
 extern "C" int gpuchan_pending(gpuchan_t *h, size_t *n)
 {
     if (!h || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
-    *n = h->last_K;
+    *n = (h->collect_seq < h->submit_seq) ? h->slotK[h->collect_seq % gpuchan::NSLOT] : 0;
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_in_flight(gpuchan_t *h)
+{
+    return h ? (int)(h->submit_seq - h->collect_seq) : GPUCHAN_E_BADARGS;
+}
+
+extern "C" int gpuchan_discard(gpuchan_t *h)
+{
+    if (!h) return set_err(GPUCHAN_E_BADARGS, "null handle");
+    if (h->collect_seq < h->submit_seq) { h->collected_slot = (int)(h->collect_seq % gpuchan::NSLOT); h->collect_seq++; }
     return GPUCHAN_OK;
 }
 
 extern "C" int gpuchan_collect(gpuchan_t *h, int16_t *pcm_host, size_t cap, size_t *n)
 {
     if (!h || !pcm_host || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
-    *n = h->last_K;
-    if (h->last_K > cap) return set_err(GPUCHAN_E_INVAL, "collect capacity %zu < %zu outputs", cap, h->last_K);
+    *n = 0;
+    if (h->collect_seq >= h->submit_seq) return GPUCHAN_OK;          /* nothing in flight */
+    const int slot = (int)(h->collect_seq % gpuchan::NSLOT);
+    const size_t K = h->slotK[slot];
+    if (K > cap) return set_err(GPUCHAN_E_INVAL, "collect capacity %zu < %zu outputs", cap, K);
     CUDA_TRY(cudaSetDevice(h->device));
-    if (h->last_K)
-        CUDA_TRY(cudaMemcpy2DAsync(pcm_host, cap * sizeof(int16_t), h->d_pcm, h->pitch * sizeof(int16_t),
-                                   h->last_K * sizeof(int16_t), h->C, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
+    if (K)
+        CUDA_TRY(cudaMemcpy2DAsync(pcm_host, cap * sizeof(int16_t), h->d_pcm[slot], h->pitch * sizeof(int16_t),
+                                   K * sizeof(int16_t), h->C, cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(cudaStreamSynchronize(h->s_out));
+    *n = K;
+    h->collected_slot = slot;
+    h->collect_seq++;
     return GPUCHAN_OK;
 }
 
 extern "C" int gpuchan_collect_iq(gpuchan_t *h, int16_t *iq_host, size_t cap, size_t *n)
 {
     if (!h || !iq_host || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
-    if (!h->d_iq) return set_err(GPUCHAN_E_INVAL, "bank was created without GPUCHAN_F_KEEP_IQ");
-    *n = h->last_K;
-    if (h->last_K > cap) return set_err(GPUCHAN_E_INVAL, "collect capacity %zu < %zu outputs", cap, h->last_K);
+    if (!(h->flags & GPUCHAN_F_KEEP_IQ)) return set_err(GPUCHAN_E_INVAL, "bank was created without GPUCHAN_F_KEEP_IQ");
+    *n = 0;
+    const int slot = h->collected_slot;
+    if (slot < 0) return GPUCHAN_OK;
+    const size_t K = h->slotK[slot];
+    if (K > cap) return set_err(GPUCHAN_E_INVAL, "collect capacity %zu < %zu outputs", cap, K);
     CUDA_TRY(cudaSetDevice(h->device));
-    if (h->last_K)
-        CUDA_TRY(cudaMemcpy2DAsync(iq_host, cap * 4, h->d_iq, h->pitch * 4, h->last_K * 4, h->C,
-                                   cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_out, h->ev_done[slot], 0));
+    if (K)
+        CUDA_TRY(cudaMemcpy2DAsync(iq_host, cap * 4, h->d_iq[slot], h->pitch * 4, K * 4, h->C,
+                                   cudaMemcpyDeviceToHost, h->s_out));
+    CUDA_TRY(cudaStreamSynchronize(h->s_out));
+    *n = K;
     return GPUCHAN_OK;
 }
 
 extern "C" int gpuchan_device_pcm(gpuchan_t *h, const int16_t **d_pcm, size_t *pitch, size_t *n)
 {
     if (!h || !d_pcm || !pitch || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
-    *d_pcm = h->d_pcm; *pitch = h->pitch; *n = h->last_K;
+    if (h->last_slot < 0) { *d_pcm = nullptr; *pitch = h->pitch; *n = 0; return GPUCHAN_OK; }
+    *d_pcm = h->d_pcm[h->last_slot]; *pitch = h->pitch; *n = h->slotK[h->last_slot];
     return GPUCHAN_OK;
 }
 
@@ -719,3 +798,30 @@ extern "C" int gpuchan_get_rot_state(gpuchan_t *h, uint32_t channel, int16_t rot
 
 extern "C" int gpuchan_engine(gpuchan_t *h) { return h ? h->engine : GPUCHAN_E_BADARGS; }
 extern "C" uint64_t gpuchan_kernel_launches(gpuchan_t *h) { return h ? h->launches : 0; }
+
+/* Optional instrumentation for bench.py's roofline: CUDA events around every launch of the dominant
+ * (FIR+FM) kernel, on the stream it is launched on. */
+extern "C" int gpuchan_timing_enable(gpuchan_t *h, int on)
+{
+    if (!h) return set_err(GPUCHAN_E_BADARGS, "null handle");
+    h->timing = on != 0;
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_timing_read(gpuchan_t *h, double *total_ms, uint64_t *nr_launches)
+{
+    if (!h || !total_ms || !nr_launches) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    double sum = 0.0;
+    uint64_t n = 0;
+    for (auto &pr : h->timed) {
+        CUDA_TRY(cudaEventSynchronize(pr.second));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        sum += ms; n++;
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    h->timed.clear();
+    *total_ms = sum; *nr_launches = n;
+    return GPUCHAN_OK;
+}

@@ -155,3 +155,19 @@ class GpuChan:
     @property
     def kernel_launches(self):
         return self._L.gpuchan_kernel_launches(self._h)
+
+    def timing_enable(self, on=True):
+        _check(self._L.gpuchan_timing_enable(self._h, 1 if on else 0), "gpuchan_timing_enable")
+
+    def timing_read(self):
+        ms = C.c_double(0)
+        n = C.c_uint64(0)
+        _check(self._L.gpuchan_timing_read(self._h, C.byref(ms), C.byref(n)), "gpuchan_timing_read")
+        return ms.value, n.value
+
+    def discard(self):
+        _check(self._L.gpuchan_discard(self._h), "gpuchan_discard")
+
+    @property
+    def in_flight(self):
+        return self._L.gpuchan_in_flight(self._h)
