@@ -192,6 +192,33 @@ __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict
     rot_state[c] = pack16(r_re, r_im);
 }
 
+/* Steady-state variant: every channel is past its transient (k0 >= mu) and has a tabulated cycle, so
+ * each (tile, channel) checkpoint is an independent table lookup. */
+__global__ void rot_prepass_table_kernel(int *__restrict__ rot_state, int nr_channels, const uint32_t *__restrict__ mu,
+                                         const uint32_t *__restrict__ lambda, const int *__restrict__ cyc,
+                                         unsigned long long k0, unsigned long long K, int KP, int nr_tiles,
+                                         int *__restrict__ ckpt)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nr_channels) return;
+    const uint32_t m = mu[c], lam = lambda[c];
+    const int *tab = cyc + (size_t)c * ROT_LMAX;
+    /* phase of the first tile, then advance by KP (mod lambda) per tile: no 64-bit division in the loop */
+    const int t_begin = blockIdx.y * 256;
+    const int t_end = min(nr_tiles, t_begin + 256);
+    if (t_begin >= nr_tiles) return;
+    const unsigned long long g0 = k0 + (unsigned long long)t_begin * KP - (t_begin > 0 ? 1 : 0);
+    uint32_t ph = (uint32_t)((g0 - m) % lam);
+    const uint32_t step = (uint32_t)(KP % (int)lam);
+    for (int t = t_begin; t < t_end; t++) {
+        ckpt[(size_t)t * nr_channels + c] = tab[ph];
+        uint32_t adv = step;
+        if (t == 0) adv = (uint32_t)((KP - 1) % (int)lam);      /* tile 0 has no leading output */
+        ph += adv; if (ph >= lam) ph -= lam;
+    }
+    if (blockIdx.y == 0) rot_state[c] = tab[(k0 + K - m) % lam];
+}
+
 /* -------------------------------------------------------------------------------------- */
 struct FirFmParams {
     InWindow in;
@@ -389,6 +416,8 @@ struct gpuchan {
     uint64_t launches = 0;
     AtanParams atan{};
     bool timing = false;
+    unsigned long long mu_max = 0;          /* all channels are on their limit cycle once k_total >= mu_max */
+    bool all_cyclic = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;   /* around each dominant-kernel launch */
 
     /* kernel variant */
@@ -554,6 +583,16 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
     h->launches++;
     FAIL_TRY(cudaGetLastError());
     FAIL_TRY(cudaStreamSynchronize(h->stream));
+    {
+        std::vector<uint32_t> mu(C), lam(C);
+        FAIL_TRY(cudaMemcpy(mu.data(), h->d_mu, C * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        FAIL_TRY(cudaMemcpy(lam.data(), h->d_lambda, C * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        h->all_cyclic = true; h->mu_max = 0;
+        for (int c = 0; c < C; c++) {
+            if (lam[c] == 0) h->all_cyclic = false;
+            else if (mu[c] > h->mu_max) h->mu_max = mu[c];
+        }
+    }
 #undef FAIL_TRY
     *ph = h;
     return GPUCHAN_OK;
@@ -607,8 +646,14 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
         const int nr_tiles = (int)((K + KP - 1) / KP);
         if ((size_t)nr_tiles > h->ckpt_tiles || K > h->pitch) return set_err(GPUCHAN_E_INVAL, "internal capacity exceeded");
 
-        rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, st>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
-                                                            h->k_total, K, KP, nr_tiles, h->d_ckpt);
+        if (h->all_cyclic && h->k_total >= h->mu_max + 1) {
+            dim3 g((h->C + 63) / 64, (nr_tiles + 255) / 256);
+            rot_prepass_table_kernel<<<g, 64, 0, st>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, KP,
+                                                       nr_tiles, h->d_ckpt);
+        } else {
+            rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, st>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
+                                                                h->k_total, K, KP, nr_tiles, h->d_ckpt);
+        }
         h->launches++;
         CUDA_TRY(cudaGetLastError());
 

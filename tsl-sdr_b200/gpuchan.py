@@ -112,15 +112,18 @@ class GpuChan:
             out = np.zeros((self.nr_channels, max(k, 1)), np.int16)
         n = C.c_size_t(0)
         _check(self._L.gpuchan_collect(self._h, out.ctypes.data, out.shape[1], C.byref(n)), "gpuchan_collect")
+        self._last_k = n.value
         return out[:, :n.value]
 
     def collect_into(self, host_ptr: int, cap_per_channel: int) -> int:
         n = C.c_size_t(0)
         _check(self._L.gpuchan_collect(self._h, host_ptr, cap_per_channel, C.byref(n)), "gpuchan_collect")
+        self._last_k = n.value
         return n.value
 
     def collect_iq(self) -> np.ndarray:
-        k = self.pending()
+        """Post-FIR IQ of the batch most recently returned by collect()."""
+        k = getattr(self, "_last_k", 0)
         out = np.zeros((self.nr_channels, max(k, 1), 2), np.int16)
         n = C.c_size_t(0)
         _check(self._L.gpuchan_collect_iq(self._h, out.ctypes.data, out.shape[1], C.byref(n)), "gpuchan_collect_iq")
