@@ -1,0 +1,105 @@
+/*
+ * tslb200_gpupager.h -- C ABI of the B200 pager bank: rational resampler + POCSAG decode for every channel
+ * of a channel bank, fed with that bank's int16 PCM.
+ *
+ * It replaces one `decoder` process per channel (decoder/decoder.c) reading a channel's FIFO:
+ *
+ *   reference seam                                          replaced by
+ *   ------------------------------------------------------  ------------------------------------
+ *   decoder/decoder.c:527-533  taps = (int16)(coef*16384)    gpupager_quantize_taps
+ *   decoder/decoder.c:685      polyphase_fir_new(I, D)       gpupager_create
+ *   decoder/decoder.c:693      pager_pocsag_new(...)         gpupager_create
+ *   decoder/decoder.c:596-632  read(fifo) -> 1024-sample buf gpupager_feed / gpupager_feed_device
+ *   filter/polyphase_fir.c:162 polyphase_fir_process         resample kernel
+ *   filter/dc_blocker.h:72     dc_blocker_apply (-b)         GPUPAGER_F_DC_BLOCK (inside the decode kernel)
+ *   pager/pager_pocsag.c:434   pager_pocsag_on_pcm           pocsag kernel (eye sync, slicer, BCH, message assembly)
+ *   pager/pager_pocsag.h:8-22  on_numeric / on_alpha         gpupager_dispatch (same argument meaning, fired on the host)
+ *
+ * Stream contract: resampled sample m of a channel exists as soon as input samples up to n_m + M are
+ * available (strict, polyphase_fir.c:184); the decoder consumes every resampled sample in order. Feeds
+ * may have any length. aresult_t-compatible returns (0 == A_OK).
+ */
+#ifndef TSLB200_GPUPAGER_H
+#define TSLB200_GPUPAGER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPUPAGER_OK           0
+#define GPUPAGER_E_NOMEM    (-1)
+#define GPUPAGER_E_BADARGS  (-2)
+#define GPUPAGER_E_INVAL    (-5)
+#define GPUPAGER_E_CUDA     (-64)
+#define GPUPAGER_E_NODEVICE (-65)
+
+#define GPUPAGER_F_DC_BLOCK   0x1u   /* decoder -b (filter/dc_blocker.h), pole from cfg.dc_pole */
+#define GPUPAGER_F_KEEP_PCM   0x2u   /* keep the resampled PCM of the last feed (decoder -d tap) */
+#define GPUPAGER_F_NO_RESAMPLE 0x4u  /* input is already at 38400 Hz: bypass the resampler */
+
+#define GPUPAGER_MSG_NUMERIC  0
+#define GPUPAGER_MSG_ALPHA    1
+#define GPUPAGER_MSG_TEXT_MAX 512
+
+typedef struct gpupager gpupager_t;
+
+typedef struct gpupager_cfg {
+    uint32_t struct_size;
+    uint32_t nr_channels;
+    int32_t  device;
+    uint32_t interpolate;         /* decoder -I */
+    uint32_t decimate;            /* decoder -D */
+    uint32_t nr_taps;             /* resampler prototype length (lpfCoeffs) */
+    uint32_t max_feed_samples;    /* largest per-channel sample count one feed may carry */
+    uint32_t flags;
+    double   dc_pole;             /* decoder -p (default 0.9999) */
+    const int16_t *taps;          /* [nr_taps] Q.14 int16 taps, see gpupager_quantize_taps */
+} gpupager_cfg;
+
+typedef struct gpupager_msg {
+    uint32_t channel;
+    uint32_t kind;                /* GPUPAGER_MSG_* */
+    uint32_t baud;                /* 512 / 1200 / 2400 */
+    uint32_t capcode;             /* as the reference reports it (pager_pocsag.c:362) */
+    uint32_t function;
+    uint32_t len;                 /* bytes in text */
+    char     text[GPUPAGER_MSG_TEXT_MAX];
+} gpupager_msg;
+
+/* Same argument meaning as pager/pager_pocsag.h:8-22, plus the channel index and a user pointer. */
+typedef int (*gpupager_on_msg_func_t)(void *user, uint32_t channel, uint16_t baud_rate, uint32_t capcode,
+                                      const char *data, size_t data_len, uint8_t function);
+
+/* decoder/decoder.c:530-533: (int16_t)(coef * (1 << 14)) */
+int gpupager_quantize_taps(const double *coeffs, size_t nr, int16_t *taps_q14);
+
+int gpupager_create(gpupager_t **ph, const gpupager_cfg *cfg);
+int gpupager_destroy(gpupager_t **ph);
+
+/* n samples per channel from device memory: channel c at d_pcm + c*pitch_samples (what
+ * gpuchan_device_pcm returns). Enqueued on cuda_stream (NULL = own stream, ordered after it otherwise). */
+int gpupager_feed_device(gpupager_t *h, const int16_t *d_pcm, size_t pitch_samples, size_t n, void *cuda_stream);
+/* Same from host memory ([nr_channels][pitch_samples] int16). */
+int gpupager_feed(gpupager_t *h, const int16_t *pcm_host, size_t pitch_samples, size_t n);
+
+/* Wait for the kernels, then hand every message decoded since the last call to the callbacks, channel by
+ * channel in decode order.  Either callback may be NULL.  Returns the number of messages in *nr_msgs. */
+int gpupager_dispatch(gpupager_t *h, gpupager_on_msg_func_t on_numeric, gpupager_on_msg_func_t on_alpha, void *user,
+                      size_t *nr_msgs);
+/* Same, copying the records instead (at most cap; the rest stay queued). */
+int gpupager_poll(gpupager_t *h, gpupager_msg *out, size_t cap, size_t *nr_msgs);
+
+/* decoder -d tap: resampled PCM of the last feed, channel c at out[c*cap ...]; needs GPUPAGER_F_KEEP_PCM. */
+int gpupager_collect_pcm(gpupager_t *h, int16_t *out, size_t cap_per_channel, size_t *n_per_channel);
+
+uint64_t gpupager_kernel_launches(gpupager_t *h);
+uint64_t gpupager_dropped_msgs(gpupager_t *h);
+const char *gpupager_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -207,6 +207,26 @@ size_t orc_resamp_stream(orc_resamp *r, const int16_t *x, size_t n, int16_t *out
 }
 
 /* ---------------------------------------------------------------------- */
+/* f1  filter/dc_blocker.h:46-92                                            */
+/* ---------------------------------------------------------------------- */
+void orc_dc_blocker_init(orc_dc_blocker *b, double pole)
+{
+    memset(b, 0, sizeof(*b));
+    b->p = (int16_t)((1.0 - pole) * (double)(1 << 14));         /* dc_blocker.h:57 */
+}
+
+void orc_dc_blocker_apply(orc_dc_blocker *b, int16_t *x, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {                            /* dc_blocker.h:79-88 */
+        b->acc = wsub(b->acc, b->x_prev);
+        b->x_prev = (int32_t)((uint32_t)(int32_t)x[i] << 14);
+        b->acc = wadd(b->acc, wsub(b->x_prev, wmul(b->p, b->y_prev)));
+        b->y_prev = b->acc >> 14;
+        x[i] = (int16_t)b->y_prev;
+    }
+}
+
+/* ---------------------------------------------------------------------- */
 /* a7  pager/bch_code.c:42-74 (field), :307-398 (decode); poly per          */
 /*     pager/pager_pocsag.c:150 : x^5 + x^2 + 1, n=31, k=21, t=2            */
 /* ---------------------------------------------------------------------- */

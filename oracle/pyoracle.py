@@ -77,6 +77,8 @@ class Oracle:
         L.orc_resamp_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                         C.POINTER(C.c_size_t)]
         L.orc_bch_decode.argtypes = [C.POINTER(C.c_uint32)]
+        L.orc_dc_blocker_init.argtypes = [C.c_void_p, C.c_double]
+        L.orc_dc_blocker_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_pocsag_new.restype = C.c_void_p
         L.orc_pocsag_new.argtypes = [C.c_size_t]
         L.orc_pocsag_delete.argtypes = [C.c_void_p]
@@ -139,6 +141,13 @@ class Oracle:
         n = self.L.orc_resamp_stream(r, pcm.ctypes.data, len(pcm), out.ctypes.data, cap, C.byref(consumed))
         self.L.orc_resamp_free(r)
         return out[:n].copy(), consumed.value
+
+    def dc_block(self, pcm, pole=0.9999):
+        out = _as_i16(pcm).copy()
+        st = (C.c_uint8 * 16)()
+        self.L.orc_dc_blocker_init(st, float(pole))
+        self.L.orc_dc_blocker_apply(st, out.ctypes.data, len(out))
+        return out
 
     def bch_decode(self, word):
         w = C.c_uint32(word)

@@ -120,3 +120,14 @@ def test_random_pcm_into_pocsag(oracle, ref):
     for pos in range(5000, 390000, 40000):
         pcm[pos:pos + len(burst)] = burst
     assert oracle.pocsag(pcm) == ref.pocsag(pcm)
+
+
+def test_dc_blocker(oracle, ref):
+    """decoder -b: resampler output through filter/dc_blocker.h (state carried across 1024-sample blocks)."""
+    rng = np.random.default_rng(12)
+    pcm = np.clip(np.round(rng.normal(900, 5000, 1024 * 8)), -32768, 32767).astype(np.int16)
+    taps = np.round(synth.lowpass_taps(97, 0.09, 1.0) * 4 * 16384).astype(np.int16)
+    for pole in (0.9999, 0.99):
+        exp = ref.resample(taps, 4, 5, pcm, use_dc=True, pole=pole)
+        got = oracle.dc_block(oracle.resample(taps, 4, 5, pcm)[0][:len(exp)], pole)
+        assert len(exp) > 1000 and np.array_equal(got, exp)

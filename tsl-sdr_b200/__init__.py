@@ -7,3 +7,4 @@ this package is only the thin ctypes mirror used by tests and bench.py.
 """
 from . import _lib          # noqa: F401
 from .gpuchan import GpuChan, prepare_taps, derot_increment, db_to_gain  # noqa: F401
+from .gpupager import GpuPager, quantize_taps  # noqa: F401

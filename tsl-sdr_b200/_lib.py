@@ -55,10 +55,38 @@ def _declare(L: C.CDLL) -> None:
     L.gpuchan_kernel_launches.restype = C.c_uint64
     L.gpuchan_kernel_launches.argtypes = [vp]
     L.gpuchan_last_error.restype = C.c_char_p
+    L.gpupager_quantize_taps.argtypes = [vp, sz, vp]
+    L.gpupager_create.argtypes = [C.POINTER(vp), C.POINTER(GpuPagerCfg)]
+    L.gpupager_destroy.argtypes = [C.POINTER(vp)]
+    L.gpupager_feed_device.argtypes = [vp, vp, sz, sz, vp]
+    L.gpupager_feed.argtypes = [vp, vp, sz, sz]
+    L.gpupager_dispatch.argtypes = [vp, ON_MSG, ON_MSG, vp, C.POINTER(sz)]
+    L.gpupager_poll.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.gpupager_collect_pcm.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.gpupager_kernel_launches.restype = C.c_uint64
+    L.gpupager_kernel_launches.argtypes = [vp]
+    L.gpupager_dropped_msgs.restype = C.c_uint64
+    L.gpupager_dropped_msgs.argtypes = [vp]
+    L.gpupager_last_error.restype = C.c_char_p
     L.gpuchan_in_flight.argtypes = [vp]
     L.gpuchan_discard.argtypes = [vp]
     L.gpuchan_timing_enable.argtypes = [vp, C.c_int]
     L.gpuchan_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+
+
+class GpuPagerCfg(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("nr_channels", C.c_uint32), ("device", C.c_int32),
+                ("interpolate", C.c_uint32), ("decimate", C.c_uint32), ("nr_taps", C.c_uint32),
+                ("max_feed_samples", C.c_uint32), ("flags", C.c_uint32), ("dc_pole", C.c_double),
+                ("taps", C.POINTER(C.c_int16))]
+
+
+class GpuPagerMsg(C.Structure):
+    _fields_ = [("channel", C.c_uint32), ("kind", C.c_uint32), ("baud", C.c_uint32), ("capcode", C.c_uint32),
+                ("function", C.c_uint32), ("len", C.c_uint32), ("text", C.c_char * 512)]
+
+
+ON_MSG = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint32, C.POINTER(C.c_char), C.c_size_t, C.c_uint8)
 
 
 # every symbol include/tslb200_gpuchan.h declares (checked by the CPU test-suite)
@@ -66,4 +94,7 @@ EXPORTS = ["gpuchan_prepare_taps", "gpuchan_derot_increment", "gpuchan_db_to_gai
            "gpuchan_destroy", "gpuchan_submit", "gpuchan_submit_device", "gpuchan_sync", "gpuchan_pending",
            "gpuchan_collect", "gpuchan_collect_iq", "gpuchan_device_pcm", "gpuchan_get_taps",
            "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error", "gpuchan_timing_enable", "gpuchan_in_flight", "gpuchan_discard",
-           "gpuchan_timing_read"]
+           "gpuchan_timing_read",
+           "gpupager_quantize_taps", "gpupager_create", "gpupager_destroy", "gpupager_feed_device", "gpupager_feed",
+           "gpupager_dispatch", "gpupager_poll", "gpupager_collect_pcm", "gpupager_kernel_launches",
+           "gpupager_dropped_msgs", "gpupager_last_error"]

@@ -1,0 +1,665 @@
+/*
+ * gpupager.cu -- B200 pager bank: rational resampler + POCSAG decoder for every channel of a channel bank.
+ * C ABI in include/tslb200_gpupager.h.
+ *
+ * Kernels:
+ *   resample_kernel   one thread per (channel, output): y_m = rq(sum_j h_{p_m}[j] * x[n_m + j]),
+ *                     n_m = floor(m*D/I), p_m = (m*D) mod I            (filter/polyphase_fir.c:184-227,
+ *                                                                       filter/utils.c:46-116)
+ *   pocsag_kernel     one thread per channel, sequential over the resampled 38400 Hz stream: optional DC
+ *                     blocker (filter/dc_blocker.h:72-92), 3-rate eye sync detector, slicer, 16-word batch,
+ *                     BCH(31,21) correction, address/alpha/numeric assembly (pager/pager_pocsag.c:82-543,
+ *                     pager/bch_code.c:307-398).  Messages are queued per channel for the host callbacks.
+ *   pcm_carry_kernel  keeps the <= M input samples per channel the next feed still needs.
+ *
+ * All arithmetic is integer/bitwise and reproduces the reference bit for bit, including its quirks:
+ * LSB-first batch words (`bit << bit_count`, count masked to 5 bits as x86 does), the bit-reversed idle
+ * word 0x6983915e, bit-reversed address/function reporting, EOT/NUL padding kept in the delivered text.
+ */
+#include "../../include/tslb200_gpupager.h"
+#include "fm_math.cuh"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace tslb200;
+
+static thread_local std::string g_pager_error;
+
+static int perr(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_pager_error = buf;
+    return code;
+}
+
+#define PCUDA(expr)                                                                                 \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return perr(GPUPAGER_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" const char *gpupager_last_error(void) { return g_pager_error.c_str(); }
+
+extern "C" int gpupager_quantize_taps(const double *coeffs, size_t nr, int16_t *taps_q14)
+{
+    if (!coeffs || !taps_q14) return perr(GPUPAGER_E_BADARGS, "null argument");
+    const double q15 = (double)(1 << 14);                       /* decoder/decoder.c:528 */
+    for (size_t i = 0; i < nr; i++) taps_q14[i] = (int16_t)(coeffs[i] * q15);   /* decoder.c:532 */
+    return GPUPAGER_OK;
+}
+
+namespace {
+
+constexpr uint32_t POCSAG_SYNC = 0x7cd215d8u;   /* pager/pager_pocsag_priv.h:40 */
+constexpr uint32_t POCSAG_IDLE = 0x6983915eu;   /* pager/pager_pocsag_priv.h:46 */
+
+enum { ST_SEARCH = 0, ST_SYNCHRONIZED = 1, ST_BATCH = 2, ST_SYNCWORD = 3 };
+enum { MT_NONE = 0, MT_UNKNOWN = 1 };
+
+/* GF(2^5), x^5 + x^2 + 1 (pager/pager_pocsag.c:150): alpha^i and discrete log */
+__constant__ uint8_t c_gf_exp[32];
+__constant__ int8_t c_gf_log[32];
+
+struct PocsagState {
+    int state;
+    uint32_t sample_skip, baud;
+    uint32_t b_skip, b_word, b_word_bit, b_bits;
+    uint32_t s_skip, s_bits, s_word;
+    uint32_t eye_cur[3], eye_matches[3];
+    uint32_t n_alpha, n_numeric;
+    int score, seen_nonprint;
+    uint32_t capcode, w_alpha, w_numeric, vb_alpha, vb_numeric, function;
+    int msg_type;
+    int dc_x, dc_y, dc_acc;
+    uint32_t batch[16];
+    uint32_t eye_reg[75 + 32 + 16];
+};
+
+struct MsgSink {
+    gpupager_msg *msgs;         /* [C][cap] */
+    uint32_t *count;            /* [C] */
+    unsigned long long *dropped;
+    uint32_t cap;               /* messages per channel between two drains */
+};
+
+struct InPcm {
+    const short *carry;         /* [C][carry_pitch] */
+    const short *fresh;         /* [C][fresh_pitch] */
+    long long carry_pitch, fresh_pitch;
+    long long carry_len, total; /* window = carry_len + fresh_len samples, starting at global index base */
+};
+
+__device__ __forceinline__ int pcm_at(const InPcm &w, int c, long long i)
+{
+    if (i < 0 || i >= w.total) return 0;
+    return (i < w.carry_len) ? (int)w.carry[(size_t)c * w.carry_pitch + i]
+                             : (int)w.fresh[(size_t)c * w.fresh_pitch + (i - w.carry_len)];
+}
+
+__global__ void resample_kernel(InPcm in, unsigned long long base, const short *__restrict__ phase_filters, int M,
+                                unsigned interp, unsigned decim, unsigned long long m0, unsigned nr_out,
+                                short *__restrict__ out, long long out_pitch)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (i >= nr_out) return;
+    const unsigned long long m = m0 + i;
+    const unsigned long long adv = m * decim;
+    const unsigned long long n_m = adv / interp;
+    const unsigned p = (unsigned)(adv % interp);
+    const short *h = phase_filters + (size_t)p * M;
+    const long long off = (long long)(n_m - base);
+    int acc = 0;
+    for (int j = 0; j < M; j++) acc += pcm_at(in, c, off + j) * (int)h[j];
+    out[(size_t)c * out_pitch + i] = (short)rq14(acc);
+}
+
+__global__ void pcm_carry_kernel(InPcm in, long long from, short *__restrict__ dst, long long dst_pitch, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (i < n) dst[(size_t)c * dst_pitch + i] = (short)pcm_at(in, c, from + i);
+}
+
+/* ---- BCH(31,21,t=2), bit (30-j) of the word = coefficient j (pager/bch_code.c:325-394) ---- */
+__device__ int bch_decode(uint32_t &word)
+{
+    uint32_t r = word;
+    int s[5];
+    bool any = false;
+#pragma unroll
+    for (int i = 1; i <= 4; i++) {
+        int v = 0;
+        for (int j = 0; j < 31; j++)
+            if ((r >> (30 - j)) & 1) v ^= c_gf_exp[(i * j) % 31];
+        any |= (v != 0);
+        s[i] = c_gf_log[v];
+    }
+    if (!any) return 0;
+    if (s[1] != -1) {
+        const int s3 = (s[1] * 3) % 31;
+        if (s[3] == s3) {
+            r ^= 1u << (30 - s[1]);
+        } else {
+            const int aux = (s[3] != -1) ? (c_gf_exp[s3] ^ c_gf_exp[s[3]]) : c_gf_exp[s3];
+            int reg1 = (s[2] - c_gf_log[aux] + 31) % 31;
+            int reg2 = (s[1] - c_gf_log[aux] + 31) % 31;
+            int loc0 = 0, loc1 = 0, count = 0;
+            for (int i = 1; i <= 31; i++) {
+                reg1 = (reg1 + 1) % 31;
+                reg2 = (reg2 + 2) % 31;
+                const int q = 1 ^ c_gf_exp[reg1] ^ c_gf_exp[reg2];
+                if (!q) { if (count == 0) loc0 = i % 31; else if (count == 1) loc1 = i % 31; count++; }
+            }
+            if (count != 2) return 1;
+            r ^= 1u << (30 - loc0);
+            r ^= 1u << (30 - loc1);
+        }
+    } else if (s[2] != -1) {
+        return 1;
+    }
+    word = r;
+    return 0;
+}
+
+__device__ void msg_reset(PocsagState &p)
+{
+    p.n_alpha = p.n_numeric = 0;
+    p.w_alpha = p.w_numeric = 0;
+    p.vb_alpha = p.vb_numeric = 0;
+    p.seen_nonprint = 0; p.score = 0;
+    p.msg_type = MT_NONE; p.function = 0;
+}
+
+__device__ void batch_reset(PocsagState &p)
+{
+    for (int i = 0; i < 16; i++) p.batch[i] = 0;
+    p.b_word = p.b_word_bit = p.b_skip = p.b_bits = 0;
+}
+
+__device__ void eyes_reset(PocsagState &p)
+{
+    for (int i = 0; i < 75 + 32 + 16; i++) p.eye_reg[i] = 0;
+    for (int i = 0; i < 3; i++) { p.eye_cur[i] = 0; p.eye_matches[i] = 0; }
+}
+
+/* pager/pager_pocsag.c:242-297 */
+__device__ void deliver(PocsagState &p, char *alpha, char *numeric, const MsgSink &sink, int c)
+{
+    if (p.msg_type == MT_NONE) return;
+    if (p.n_alpha != 0) {
+        const char last = alpha[p.n_alpha - 1];
+        if (last == 0x4 || last == 0x3 || last == 0x0 || last == 0x17) p.score = 1;
+    }
+    if (p.n_numeric > 40) p.score = 1;
+    const bool is_alpha = p.score > 0;
+    const uint32_t slot = sink.count[c];
+    if (slot < sink.cap) {
+        gpupager_msg *m = sink.msgs + (size_t)c * sink.cap + slot;
+        m->channel = c; m->kind = is_alpha ? GPUPAGER_MSG_ALPHA : GPUPAGER_MSG_NUMERIC;
+        m->baud = p.baud; m->capcode = p.capcode; m->function = p.function;
+        const uint32_t len = is_alpha ? p.n_alpha : p.n_numeric;
+        m->len = len;
+        const char *src = is_alpha ? alpha : numeric;
+        for (uint32_t i = 0; i < len; i++) m->text[i] = src[i];
+        if (len < GPUPAGER_MSG_TEXT_MAX) m->text[len] = 0;
+        sink.count[c] = slot + 1;
+    } else {
+        atomicAdd(sink.dropped, 1ull);
+    }
+    msg_reset(p);
+}
+
+/* pager/pager_pocsag.c:320-432 */
+__device__ void process_batch(PocsagState &p, char *alpha, char *numeric, const MsgSink &sink, int c)
+{
+    const char bcd_map[16] = { '0', '1', '2', '3', '4', '5', '6', '7', '8', '9', 'X', 'U', ' ', '-', '[', ']' };
+    for (unsigned z = 0; z < 16; z++) {
+        uint32_t w = p.batch[z] & 0x7fffffffu;
+        if (bch_decode(w)) {
+            if (p.msg_type != MT_NONE) deliver(p, alpha, numeric, sink, c);
+            return;
+        }
+        if (w == POCSAG_IDLE) {
+            if (p.msg_type != MT_NONE) deliver(p, alpha, numeric, sink, c);
+            continue;
+        }
+        if ((w & 1) == 0) {
+            deliver(p, alpha, numeric, sink, c);
+            p.msg_type = MT_UNKNOWN;
+            p.function = (w >> 19) & 0x3;
+            p.capcode = (((w >> 1) & 0x3ffffu) << 3) + ((z >> 1) & 0x7);
+        } else if (p.msg_type == MT_UNKNOWN) {
+            const uint32_t val = (w >> 1) & 0xfffffu;
+            p.w_alpha |= val << p.vb_alpha;
+            p.vb_alpha += 20;
+            while (p.vb_alpha >= 7) {
+                const char ch = (char)(p.w_alpha & 0x7f);
+                if (p.n_alpha < 511) alpha[p.n_alpha++] = ch;       /* the reference buffer is 512 bytes, unchecked */
+                if ((ch >= 0x20 && ch <= 0x7e) || ch == 0xa || ch == 0xd) {
+                    if (!p.seen_nonprint) p.score++;
+                } else {
+                    p.seen_nonprint = 1;
+                    if (ch != 0x03 && ch != 0x04 && ch != 0x17 && ch != 0x0) p.score -= 10;
+                }
+                p.w_alpha >>= 7;
+                p.vb_alpha -= 7;
+            }
+            if (p.n_numeric < 511) {
+                p.w_numeric |= val << p.vb_numeric;
+                p.vb_numeric += 20;
+                while (p.vb_numeric >= 4 && p.n_numeric < 511) {
+                    numeric[p.n_numeric++] = bcd_map[p.w_numeric & 0xf];
+                    p.w_numeric >>= 4;
+                    p.vb_numeric -= 4;
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ bool sync_ok(uint32_t w) { return __popc(w ^ POCSAG_SYNC) <= 4; }
+
+/* pager/pager_pocsag.c:82-117 */
+__device__ __forceinline__ void eye_on_sample(PocsagState &p, int which, int reg_base, uint32_t spb, uint32_t baud, uint32_t bit)
+{
+    uint32_t &r = p.eye_reg[reg_base + p.eye_cur[which]];
+    r = (r << 1) | bit;
+    if (sync_ok(r)) {
+        p.eye_matches[which]++;
+    } else if (p.eye_matches[which] > spb / 2) {
+        p.sample_skip = spb;
+        p.baud = baud;
+        batch_reset(p);
+        p.b_skip = (p.eye_matches[which] / 2) & 0xffffu;
+        p.state = ST_SYNCHRONIZED;
+    } else {
+        p.eye_matches[which] = 0;
+    }
+    p.eye_cur[which] = (p.eye_cur[which] + 1) % spb;
+}
+
+__global__ void pocsag_kernel(PocsagState *__restrict__ states, char *__restrict__ text, int nr_channels,
+                              short *__restrict__ pcm, long long pitch, unsigned n, MsgSink sink, int use_dc, int dc_p)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nr_channels) return;
+    PocsagState &g = states[c];
+    PocsagState p = g;                      /* working copy (registers / local memory) */
+    char *alpha = text + (size_t)c * 1024, *numeric = alpha + 512;   /* message_alpha[512], message_numeric[512] */
+    short *x = pcm + (size_t)c * pitch;
+
+    for (unsigned i = 0; i < n; i++) {
+        int sample = x[i];
+        if (use_dc) {                       /* filter/dc_blocker.h:79-88 */
+            p.dc_acc -= p.dc_x;
+            p.dc_x = sample << 14;
+            p.dc_acc += p.dc_x - dc_p * p.dc_y;
+            p.dc_y = p.dc_acc >> 14;
+            sample = (int)(short)p.dc_y;
+            x[i] = (short)sample;
+        }
+        const uint32_t bit = sample < 0 ? 1u : 0u;
+        /* one sample through the 4-state machine (pager/pager_pocsag.c:434-543) */
+        if (p.state == ST_SYNCHRONIZED) p.state = ST_BATCH;
+        switch (p.state) {
+        case ST_SEARCH:
+            eye_on_sample(p, 0, 0, 75, 512, bit);
+            eye_on_sample(p, 1, 75, 32, 1200, bit);
+            eye_on_sample(p, 2, 75 + 32, 16, 2400, bit);
+            break;
+        case ST_BATCH:
+            p.b_skip = (p.b_skip + 1) & 0xffffu;
+            if (p.b_skip == p.sample_skip) {
+                p.batch[p.b_word] |= bit << (p.b_bits & 31);
+                p.b_word_bit++; p.b_bits = (p.b_bits + 1) & 0xffffu; p.b_skip = 0;
+                if (p.b_word_bit == 32) {
+                    p.b_word_bit = 0;
+                    if (++p.b_word == 16) {
+                        process_batch(p, alpha, numeric, sink, c);
+                        p.state = ST_SYNCWORD;
+                        p.b_word = 0;
+                        p.s_skip = 0; p.s_bits = 0; p.s_word = 0;
+                    }
+                }
+            }
+            break;
+        case ST_SYNCWORD:
+            p.s_skip = (p.s_skip + 1) & 0xffffu;
+            if (p.s_skip == p.sample_skip) {
+                p.s_skip = 0;
+                p.s_word = (p.s_word << 1) | bit;
+                if (++p.s_bits == 32) {
+                    if (!sync_ok(p.s_word)) {
+                        p.state = ST_SEARCH;
+                        p.sample_skip = 0;
+                        eyes_reset(p);
+                        deliver(p, alpha, numeric, sink, c);
+                    } else {
+                        p.state = ST_BATCH;
+                        batch_reset(p);
+                    }
+                }
+            }
+            break;
+        }
+    }
+    /* write the scalar state and small arrays back; text buffers were written in place */
+    g.state = p.state; g.sample_skip = p.sample_skip; g.baud = p.baud;
+    g.b_skip = p.b_skip; g.b_word = p.b_word; g.b_word_bit = p.b_word_bit; g.b_bits = p.b_bits;
+    g.s_skip = p.s_skip; g.s_bits = p.s_bits; g.s_word = p.s_word;
+    for (int i = 0; i < 3; i++) { g.eye_cur[i] = p.eye_cur[i]; g.eye_matches[i] = p.eye_matches[i]; }
+    g.n_alpha = p.n_alpha; g.n_numeric = p.n_numeric; g.score = p.score; g.seen_nonprint = p.seen_nonprint;
+    g.capcode = p.capcode; g.w_alpha = p.w_alpha; g.w_numeric = p.w_numeric; g.vb_alpha = p.vb_alpha;
+    g.vb_numeric = p.vb_numeric; g.function = p.function; g.msg_type = p.msg_type;
+    g.dc_x = p.dc_x; g.dc_y = p.dc_y; g.dc_acc = p.dc_acc;
+    for (int i = 0; i < 16; i++) g.batch[i] = p.batch[i];
+    for (int i = 0; i < 75 + 32 + 16; i++) g.eye_reg[i] = p.eye_reg[i];
+}
+
+} // namespace
+
+/* ------------------------------------------------------------------------------------------ */
+struct gpupager {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_own = nullptr, ev_ext = nullptr;
+    int C = 0;
+    unsigned interp = 1, decim = 1;
+    int M = 0;                          /* taps per phase */
+    uint32_t flags = 0;
+    size_t max_feed = 0;
+    int dc_p = 0;
+
+    short *d_phase = nullptr;           /* [interp][M] */
+    short *d_carry[2] = { nullptr, nullptr };
+    long long carry_pitch = 0, carry_len = 0;
+    int pp = 0;
+    unsigned long long in_base = 0;     /* global index of window sample 0 */
+    unsigned long long total_in = 0;    /* samples fed so far */
+    unsigned long long m_next = 0;      /* next resampled output index */
+    short *d_stage = nullptr;           /* host feeds: [C][max_feed] */
+    short *d_res = nullptr;             /* resampled output of the last feed [C][res_pitch] */
+    long long res_pitch = 0;
+    size_t last_out = 0;
+    PocsagState *d_states = nullptr;
+    char *d_text = nullptr;
+    uint32_t msg_cap = 32;
+    gpupager_msg *d_msgs = nullptr;
+    uint32_t *d_count = nullptr;
+    unsigned long long *d_dropped = nullptr;
+    std::vector<gpupager_msg> queue;    /* decoded, not yet handed out */
+    uint64_t launches = 0, dropped = 0;
+};
+
+static void pager_free(gpupager *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_phase); cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_stage); cudaFree(h->d_res);
+    cudaFree(h->d_states); cudaFree(h->d_text); cudaFree(h->d_msgs); cudaFree(h->d_count); cudaFree(h->d_dropped);
+    if (h->ev_own) cudaEventDestroy(h->ev_own);
+    if (h->ev_ext) cudaEventDestroy(h->ev_ext);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int gpupager_create(gpupager_t **ph, const gpupager_cfg *cfg)
+{
+    if (!ph || !cfg) return perr(GPUPAGER_E_BADARGS, "null argument");
+    *ph = nullptr;
+    if (cfg->struct_size != sizeof(gpupager_cfg)) return perr(GPUPAGER_E_BADARGS, "gpupager_cfg size mismatch");
+    const bool bypass = (cfg->flags & GPUPAGER_F_NO_RESAMPLE) != 0;
+    if (!cfg->nr_channels || !cfg->max_feed_samples) return perr(GPUPAGER_E_BADARGS, "incomplete configuration");
+    if (!bypass && (!cfg->interpolate || !cfg->decimate || !cfg->nr_taps || !cfg->taps))
+        return perr(GPUPAGER_E_BADARGS, "resampler needs interpolate, decimate and taps");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return perr(GPUPAGER_E_NODEVICE, "no CUDA device: this library has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return perr(GPUPAGER_E_BADARGS, "bad device ordinal");
+    PCUDA(cudaSetDevice(cfg->device));
+
+    gpupager *h = new (std::nothrow) gpupager();
+    if (!h) return perr(GPUPAGER_E_NOMEM, "out of memory");
+    h->device = cfg->device; h->C = (int)cfg->nr_channels; h->flags = cfg->flags; h->max_feed = cfg->max_feed_samples;
+    if (cfg->flags & GPUPAGER_F_DC_BLOCK) {
+        const double pole = cfg->dc_pole != 0.0 ? cfg->dc_pole : 0.9999;
+        h->dc_p = (int16_t)((1.0 - pole) * (double)(1 << 14));      /* filter/dc_blocker.h:57 */
+    }
+#define PFAIL(expr)                                                                                 \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            perr(GPUPAGER_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            pager_free(h);                                                                          \
+            return GPUPAGER_E_CUDA;                                                                 \
+        }                                                                                           \
+    } while (0)
+    PFAIL(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    PFAIL(cudaEventCreateWithFlags(&h->ev_own, cudaEventDisableTiming));
+    PFAIL(cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming));
+
+    const int C = h->C;
+    size_t max_out = h->max_feed;
+    if (!bypass) {
+        h->interp = cfg->interpolate; h->decim = cfg->decimate;
+        size_t m = (cfg->nr_taps + h->interp - 1) / h->interp;      /* polyphase_fir.c:70 */
+        m = (m + 3) & ~(size_t)3;                                   /* polyphase_fir.c:73 */
+        h->M = (int)m;
+        std::vector<short> phases((size_t)h->interp * m, 0);
+        for (size_t i = 0; i < cfg->nr_taps; i++)                   /* polyphase_fir.c:81-83 */
+            phases[(i % h->interp) * m + i / h->interp] = cfg->taps[i];
+        PFAIL(cudaMalloc(&h->d_phase, phases.size() * sizeof(short)));
+        PFAIL(cudaMemcpy(h->d_phase, phases.data(), phases.size() * sizeof(short), cudaMemcpyHostToDevice));
+        h->carry_pitch = (long long)((m + 8 + 7) & ~(size_t)7);
+        for (int i = 0; i < 2; i++) PFAIL(cudaMalloc(&h->d_carry[i], (size_t)C * h->carry_pitch * sizeof(short)));
+        max_out = (h->max_feed + m) * h->interp / h->decim + 8;
+    }
+    h->res_pitch = (long long)((max_out + 63) & ~(size_t)63);
+    PFAIL(cudaMalloc(&h->d_res, (size_t)C * h->res_pitch * sizeof(short)));
+    PFAIL(cudaMalloc(&h->d_stage, (size_t)C * h->max_feed * sizeof(short)));
+    PFAIL(cudaMalloc(&h->d_states, (size_t)C * sizeof(PocsagState)));
+    PFAIL(cudaMemset(h->d_states, 0, (size_t)C * sizeof(PocsagState)));
+    PFAIL(cudaMalloc(&h->d_text, (size_t)C * 1024));
+    PFAIL(cudaMemset(h->d_text, 0, (size_t)C * 1024));
+    h->msg_cap = 32 + (uint32_t)(max_out / 1000);       /* shortest message: 2 codewords x 16 samples/bit */
+    PFAIL(cudaMalloc(&h->d_msgs, (size_t)C * h->msg_cap * sizeof(gpupager_msg)));
+    PFAIL(cudaMalloc(&h->d_count, C * sizeof(uint32_t)));
+    PFAIL(cudaMemset(h->d_count, 0, C * sizeof(uint32_t)));
+    PFAIL(cudaMalloc(&h->d_dropped, sizeof(unsigned long long)));
+    PFAIL(cudaMemset(h->d_dropped, 0, sizeof(unsigned long long)));
+
+    /* GF(2^5) tables, primitive polynomial x^5 + x^2 + 1 */
+    uint8_t gexp[32]; int8_t glog[32];
+    int v = 1;
+    for (int i = 0; i < 31; i++) { gexp[i] = (uint8_t)v; glog[v] = (int8_t)i; v <<= 1; if (v & 0x20) v ^= 0x25; }
+    gexp[31] = 0; glog[0] = -1;
+    PFAIL(cudaMemcpyToSymbol(c_gf_exp, gexp, sizeof(gexp)));
+    PFAIL(cudaMemcpyToSymbol(c_gf_log, glog, sizeof(glog)));
+#undef PFAIL
+    *ph = h;
+    return GPUPAGER_OK;
+}
+
+extern "C" int gpupager_destroy(gpupager_t **ph)
+{
+    if (!ph || !*ph) return perr(GPUPAGER_E_BADARGS, "null handle");
+    cudaSetDevice((*ph)->device);
+    cudaStreamSynchronize((*ph)->stream);
+    pager_free(*ph);
+    *ph = nullptr;
+    return GPUPAGER_OK;
+}
+
+static int pager_run(gpupager *h, const short *d_pcm, size_t pitch, size_t n, cudaStream_t st)
+{
+    const int C = h->C;
+    const short *dec_in = d_pcm;
+    long long dec_pitch = (long long)pitch;
+    unsigned nr_dec = (unsigned)n;
+
+    if (!(h->flags & GPUPAGER_F_NO_RESAMPLE)) {
+        InPcm in;
+        in.carry = h->d_carry[h->pp]; in.fresh = d_pcm;
+        in.carry_pitch = h->carry_pitch; in.fresh_pitch = (long long)pitch;
+        in.carry_len = h->carry_len; in.total = h->carry_len + (long long)n;
+        const unsigned long long total = h->total_in + n;
+        /* outputs m with n_m + M < total  <=>  m < (total - M) * I / D   (polyphase_fir.c:184, strict) */
+        unsigned long long m_end = h->m_next;
+        if (total > (unsigned long long)h->M) {
+            const unsigned long long lim = (total - h->M) * h->interp;          /* m * D < lim */
+            m_end = (lim + h->decim - 1) / h->decim;
+            if (m_end < h->m_next) m_end = h->m_next;
+        }
+        const unsigned long long nr_out = m_end - h->m_next;
+        if (nr_out > (unsigned long long)h->res_pitch) return perr(GPUPAGER_E_INVAL, "feed too large for the output buffer");
+        if (nr_out) {
+            dim3 grid((unsigned)((nr_out + 255) / 256), C);
+            resample_kernel<<<grid, 256, 0, st>>>(in, h->in_base, h->d_phase, h->M, h->interp, h->decim, h->m_next,
+                                                  (unsigned)nr_out, h->d_res, h->res_pitch);
+            h->launches++;
+            PCUDA(cudaGetLastError());
+        }
+        h->m_next = m_end;
+        h->total_in = total;
+        /* keep input from n_next on */
+        unsigned long long n_next = h->m_next * h->decim / h->interp;
+        if (n_next > total) n_next = total;
+        if (n_next < h->in_base) n_next = h->in_base;
+        const long long keep = (long long)(total - n_next);
+        if (keep > h->carry_pitch) return perr(GPUPAGER_E_INVAL, "internal: carry %lld exceeds capacity", keep);
+        if (keep > 0) {
+            dim3 grid((unsigned)((keep + 63) / 64), C);
+            pcm_carry_kernel<<<grid, 64, 0, st>>>(in, (long long)(n_next - h->in_base), h->d_carry[h->pp ^ 1], h->carry_pitch, (int)keep);
+            h->launches++;
+            PCUDA(cudaGetLastError());
+        }
+        h->pp ^= 1;
+        h->carry_len = keep;
+        h->in_base = n_next;
+        dec_in = h->d_res; dec_pitch = h->res_pitch; nr_dec = (unsigned)nr_out;
+    } else if (h->flags & (GPUPAGER_F_DC_BLOCK | GPUPAGER_F_KEEP_PCM)) {
+        /* the decoder may rewrite samples in place (DC blocker) and the -d tap wants them: work on a copy */
+        if (n > (size_t)h->res_pitch) return perr(GPUPAGER_E_INVAL, "feed too large");
+        PCUDA(cudaMemcpy2DAsync(h->d_res, h->res_pitch * sizeof(short), d_pcm, pitch * sizeof(short), n * sizeof(short), C,
+                                cudaMemcpyDeviceToDevice, st));
+        dec_in = h->d_res; dec_pitch = h->res_pitch;
+    }
+    h->last_out = nr_dec;
+    if (nr_dec) {
+        MsgSink sink{ h->d_msgs, h->d_count, h->d_dropped, h->msg_cap };
+        pocsag_kernel<<<(C + 31) / 32, 32, 0, st>>>(h->d_states, h->d_text, C, const_cast<short *>(dec_in), dec_pitch, nr_dec, sink,
+                                                    (h->flags & GPUPAGER_F_DC_BLOCK) ? 1 : 0, h->dc_p);
+        h->launches++;
+        PCUDA(cudaGetLastError());
+    }
+    return GPUPAGER_OK;
+}
+
+extern "C" int gpupager_feed_device(gpupager_t *h, const int16_t *d_pcm, size_t pitch, size_t n, void *cuda_stream)
+{
+    if (!h || (!d_pcm && n)) return perr(GPUPAGER_E_BADARGS, "null argument");
+    if (n > h->max_feed) return perr(GPUPAGER_E_INVAL, "feed of %zu samples exceeds max_feed_samples %zu", n, h->max_feed);
+    if (n == 0) return GPUPAGER_OK;
+    PCUDA(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (st != h->stream) {
+        PCUDA(cudaEventRecord(h->ev_own, h->stream));
+        PCUDA(cudaStreamWaitEvent(st, h->ev_own, 0));
+    }
+    if (int rc = pager_run(h, d_pcm, pitch, n, st)) return rc;
+    if (st != h->stream) {
+        PCUDA(cudaEventRecord(h->ev_ext, st));
+        PCUDA(cudaStreamWaitEvent(h->stream, h->ev_ext, 0));
+    }
+    return GPUPAGER_OK;
+}
+
+extern "C" int gpupager_feed(gpupager_t *h, const int16_t *pcm_host, size_t pitch, size_t n)
+{
+    if (!h || (!pcm_host && n)) return perr(GPUPAGER_E_BADARGS, "null argument");
+    if (n > h->max_feed) return perr(GPUPAGER_E_INVAL, "feed of %zu samples exceeds max_feed_samples %zu", n, h->max_feed);
+    if (n == 0) return GPUPAGER_OK;
+    PCUDA(cudaSetDevice(h->device));
+    PCUDA(cudaMemcpy2DAsync(h->d_stage, h->max_feed * sizeof(short), pcm_host, pitch * sizeof(short), n * sizeof(short),
+                            h->C, cudaMemcpyHostToDevice, h->stream));
+    return pager_run(h, h->d_stage, h->max_feed, n, h->stream);
+}
+
+static int pager_drain(gpupager *h)
+{
+    PCUDA(cudaSetDevice(h->device));
+    PCUDA(cudaStreamSynchronize(h->stream));
+    std::vector<uint32_t> cnt(h->C);
+    PCUDA(cudaMemcpy(cnt.data(), h->d_count, h->C * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    bool any = false;
+    for (int c = 0; c < h->C; c++) {
+        if (!cnt[c]) continue;
+        any = true;
+        const size_t at = h->queue.size();
+        h->queue.resize(at + cnt[c]);
+        PCUDA(cudaMemcpy(&h->queue[at], h->d_msgs + (size_t)c * h->msg_cap, cnt[c] * sizeof(gpupager_msg),
+                         cudaMemcpyDeviceToHost));
+    }
+    if (any) PCUDA(cudaMemset(h->d_count, 0, h->C * sizeof(uint32_t)));
+    unsigned long long d = 0;
+    PCUDA(cudaMemcpy(&d, h->d_dropped, sizeof(d), cudaMemcpyDeviceToHost));
+    h->dropped = d;
+    return GPUPAGER_OK;
+}
+
+extern "C" int gpupager_poll(gpupager_t *h, gpupager_msg *out, size_t cap, size_t *nr_msgs)
+{
+    if (!h || !nr_msgs || (!out && cap)) return perr(GPUPAGER_E_BADARGS, "null argument");
+    if (int rc = pager_drain(h)) return rc;
+    const size_t n = h->queue.size() < cap ? h->queue.size() : cap;
+    if (n) memcpy(out, h->queue.data(), n * sizeof(gpupager_msg));
+    h->queue.erase(h->queue.begin(), h->queue.begin() + n);
+    *nr_msgs = n;
+    return GPUPAGER_OK;
+}
+
+extern "C" int gpupager_dispatch(gpupager_t *h, gpupager_on_msg_func_t on_numeric, gpupager_on_msg_func_t on_alpha, void *user,
+                                 size_t *nr_msgs)
+{
+    if (!h) return perr(GPUPAGER_E_BADARGS, "null handle");
+    if (int rc = pager_drain(h)) return rc;
+    for (const gpupager_msg &m : h->queue) {
+        gpupager_on_msg_func_t cb = (m.kind == GPUPAGER_MSG_ALPHA) ? on_alpha : on_numeric;
+        if (cb) cb(user, m.channel, (uint16_t)m.baud, m.capcode, m.text, m.len, (uint8_t)m.function);
+    }
+    if (nr_msgs) *nr_msgs = h->queue.size();
+    h->queue.clear();
+    return GPUPAGER_OK;
+}
+
+extern "C" int gpupager_collect_pcm(gpupager_t *h, int16_t *out, size_t cap, size_t *n)
+{
+    if (!h || !out || !n) return perr(GPUPAGER_E_BADARGS, "null argument");
+    if (!(h->flags & GPUPAGER_F_KEEP_PCM)) return perr(GPUPAGER_E_INVAL, "bank was created without GPUPAGER_F_KEEP_PCM");
+    *n = h->last_out;
+    if (h->last_out > cap) return perr(GPUPAGER_E_INVAL, "capacity %zu < %zu samples", cap, h->last_out);
+    PCUDA(cudaSetDevice(h->device));
+    if (h->last_out)
+        PCUDA(cudaMemcpy2DAsync(out, cap * sizeof(short), h->d_res, h->res_pitch * sizeof(short), h->last_out * sizeof(short),
+                                h->C, cudaMemcpyDeviceToHost, h->stream));
+    PCUDA(cudaStreamSynchronize(h->stream));
+    return GPUPAGER_OK;
+}
+
+extern "C" uint64_t gpupager_kernel_launches(gpupager_t *h) { return h ? h->launches : 0; }
+extern "C" uint64_t gpupager_dropped_msgs(gpupager_t *h) { return h ? h->dropped : 0; }

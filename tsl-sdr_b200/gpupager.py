@@ -1,0 +1,109 @@
+"""ctypes mirror of include/tslb200_gpupager.h (resampler + POCSAG decode for every channel)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+F_DC_BLOCK, F_KEEP_PCM, F_NO_RESAMPLE = 0x1, 0x2, 0x4
+
+
+class GpuPagerError(RuntimeError):
+    def __init__(self, code, where):
+        msg = _lib.lib().gpupager_last_error()
+        super().__init__(f"{where} failed: {code} ({msg.decode() if msg else ''})")
+        self.code = code
+
+
+def _check(code, where):
+    if code != 0:
+        raise GpuPagerError(code, where)
+
+
+def quantize_taps(coeffs):
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+    out = np.zeros(len(coeffs), np.int16)
+    _check(_lib.lib().gpupager_quantize_taps(coeffs.ctypes.data, len(coeffs), out.ctypes.data), "gpupager_quantize_taps")
+    return out
+
+
+class GpuPager:
+    def __init__(self, nr_channels, max_feed_samples, taps_q14=None, interpolate=1, decimate=1, device=0, flags=0,
+                 dc_pole=0.9999):
+        L = self._L = _lib.lib()
+        cfg = _lib.GpuPagerCfg()
+        cfg.struct_size = C.sizeof(_lib.GpuPagerCfg)
+        cfg.nr_channels = int(nr_channels)
+        cfg.device = int(device)
+        cfg.interpolate = int(interpolate)
+        cfg.decimate = int(decimate)
+        self._taps = None if taps_q14 is None else np.ascontiguousarray(taps_q14, dtype=np.int16)
+        cfg.nr_taps = 0 if self._taps is None else len(self._taps)
+        cfg.max_feed_samples = int(max_feed_samples)
+        cfg.flags = int(flags)
+        cfg.dc_pole = float(dc_pole)
+        cfg.taps = None if self._taps is None else self._taps.ctypes.data_as(C.POINTER(C.c_int16))
+        self._h = C.c_void_p()
+        _check(L.gpupager_create(C.byref(self._h), C.byref(cfg)), "gpupager_create")
+        self.nr_channels = int(nr_channels)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.gpupager_destroy(C.byref(self._h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def feed(self, pcm: np.ndarray):
+        """pcm: [nr_channels, n] int16 in host memory."""
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.nr_channels
+        pcm = np.ascontiguousarray(pcm)
+        _check(self._L.gpupager_feed(self._h, pcm.ctypes.data, pcm.shape[1], pcm.shape[1]), "gpupager_feed")
+
+    def feed_device(self, dev_ptr, pitch, n, stream=0):
+        _check(self._L.gpupager_feed_device(self._h, dev_ptr, pitch, n, stream), "gpupager_feed_device")
+
+    def poll(self, cap=4096):
+        arr = (_lib.GpuPagerMsg * cap)()
+        n = C.c_size_t(0)
+        _check(self._L.gpupager_poll(self._h, arr, cap, C.byref(n)), "gpupager_poll")
+        out = []
+        for i in range(n.value):
+            m = arr[i]
+            raw = C.string_at(C.addressof(m) + _lib.GpuPagerMsg.text.offset, min(m.len, 512))
+            out.append((m.channel, m.kind, m.baud, m.capcode, m.function, m.len, raw))
+        return out
+
+    def dispatch(self):
+        """Fires the C callbacks (same argument meaning as pager/pager_pocsag.h) and returns what they received."""
+        got = []
+
+        def mk(kind):
+            def cb(user, channel, baud, capcode, data, length, function):
+                got.append((channel, kind, baud, capcode, function, length, C.string_at(data, length)))
+                return 0
+            return _lib.ON_MSG(cb)
+        on_num, on_alpha = mk(0), mk(1)
+        n = C.c_size_t(0)
+        _check(self._L.gpupager_dispatch(self._h, on_num, on_alpha, None, C.byref(n)), "gpupager_dispatch")
+        assert n.value == len(got)
+        return got
+
+    def collect_pcm(self, cap):
+        out = np.zeros((self.nr_channels, cap), np.int16)
+        n = C.c_size_t(0)
+        _check(self._L.gpupager_collect_pcm(self._h, out.ctypes.data, cap, C.byref(n)), "gpupager_collect_pcm")
+        return out[:, :n.value]
+
+    @property
+    def kernel_launches(self):
+        return self._L.gpupager_kernel_launches(self._h)
+
+    @property
+    def dropped(self):
+        return self._L.gpupager_dropped_msgs(self._h)
