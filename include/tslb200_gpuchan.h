@@ -120,6 +120,11 @@ int gpuchan_engine(gpuchan_t *h);           /* engine actually in use */
 uint64_t gpuchan_kernel_launches(gpuchan_t *h);  /* kernels launched by this bank so far */
 const char *gpuchan_last_error(void);
 
+/* Page-locked host buffers (cudaHostAlloc) for callers that do not include CUDA headers: the receiver's
+ * batch staging (replaces the frame_alloc pool as the H2D source). */
+int gpuchan_host_alloc(void **pp, size_t bytes);
+int gpuchan_host_free(void *p);
+
 /* Instrumentation (bench.py roofline): CUDA events around each launch of the dominant FIR+FM kernel. */
 int gpuchan_timing_enable(gpuchan_t *h, int on);
 int gpuchan_timing_read(gpuchan_t *h, double *total_ms, uint64_t *nr_launches);

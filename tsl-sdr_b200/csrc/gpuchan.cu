@@ -870,3 +870,17 @@ extern "C" int gpuchan_timing_read(gpuchan_t *h, double *total_ms, uint64_t *nr_
     *total_ms = sum; *nr_launches = n;
     return GPUCHAN_OK;
 }
+
+/* Pinned host memory for callers that stay free of CUDA headers (the C host side). */
+extern "C" int gpuchan_host_alloc(void **pp, size_t bytes)
+{
+    if (!pp || !bytes) return set_err(GPUCHAN_E_BADARGS, "bad argument");
+    CUDA_TRY(cudaHostAlloc(pp, bytes, cudaHostAllocDefault));
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_host_free(void *p)
+{
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return GPUCHAN_OK;
+}
