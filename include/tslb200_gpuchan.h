@@ -129,6 +129,12 @@ int gpuchan_host_free(void *p);
 int gpuchan_timing_enable(gpuchan_t *h, int on);
 int gpuchan_timing_read(gpuchan_t *h, double *total_ms, uint64_t *nr_launches);
 
+/* Unit hook for tests: one tcgen05 kind::i8 tile, D[128][N] = A0*B0[shift0..]^T + A1*B1[shift1..]^T (int32, wraps).
+ * All pointers are host pointers; A is 128 x Kp bytes, B is R x Kp bytes, row-major. */
+int gpuchan_tc_selftest(const uint8_t *A0, const uint8_t *B0, const uint8_t *A1, const uint8_t *B1, int Kp, int R,
+                        int N, int shift0, int shift1, int a0_signed, int b0_signed, int a1_signed, int b1_signed,
+                        int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif
