@@ -9,15 +9,24 @@ import pytest
 
 from conftest import rand_iq
 from tsl_sdr_b200 import synth
-from tsl_sdr_b200.gpuchan import GpuChan, F_ATAN_FMA, F_KEEP_IQ
+from tsl_sdr_b200.gpuchan import GpuChan, GpuChanError, F_ATAN_FMA, F_KEEP_IQ, ENGINE_IMAD, ENGINE_TC
 
 pytestmark = pytest.mark.gpu
 
 
-def run_bank(lpf, offs, fs, D, iq, chunks=None, gains=None, flags=F_ATAN_FMA | F_KEEP_IQ, max_batch=None):
+ENGINES = [pytest.param(ENGINE_IMAD, id="imad"), pytest.param(ENGINE_TC, id="tc")]
+
+
+def run_bank(lpf, offs, fs, D, iq, chunks=None, gains=None, flags=F_ATAN_FMA | F_KEEP_IQ, max_batch=None, engine=ENGINE_IMAD):
     n = len(iq) // 2
     chunks = chunks or [n]
-    bank = GpuChan(lpf, offs, fs, D, max_batch or max(chunks), gains=gains, flags=flags)
+    try:
+        bank = GpuChan(lpf, offs, fs, D, max_batch or max(chunks), gains=gains, flags=flags, engine=engine)
+    except GpuChanError as exc:
+        if engine == ENGINE_TC and exc.code == -5 and "tensor-core engine unavailable" in str(exc):
+            pytest.skip(str(exc))
+        raise
+    assert bank.engine == engine
     pcm, yiq = [], []
     pos = 0
     for c in chunks:
@@ -60,17 +69,19 @@ def assert_same(got_pcm, got_iq, exp_pcm, exp_iq):
 @pytest.mark.parametrize("C,T,D,fs", [(1, 127, 100, 2400000), (5, 127, 25, 1200000), (33, 63, 16, 1000000),
                                       (64, 127, 100, 2400000), (70, 255, 200, 10000000), (3, 512, 120, 3000000),
                                       (40, 512, 120, 3000000), (2, 2, 1, 48000), (4, 33, 33, 250000)])
-def test_noise_one_shot(oracle, C, T, D, fs):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_noise_one_shot(oracle, C, T, D, fs, engine):
     n = 40000 + 7 * D + 3
     iq = rand_iq(n, seed=C * 1000 + T)
     lpf = synth.lowpass_taps(T, min(9000.0, fs / 8), fs) if T > 2 else np.array([0.5, 0.5])
     offs = synth.channel_offsets(C, fs)
-    pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq)
+    pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq, engine=engine)
     exp_pcm, exp_iq = oracle_bank(oracle, lpf, offs, fs, D, iq)
     assert_same(pcm, yiq, exp_pcm, exp_iq)
 
 
-def test_chunked_equals_one_shot(oracle):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_chunked_equals_one_shot(oracle, engine):
     """4096-sample sample_bufs (multifm/file_if.c:18), ragged tails and sub-T chunks give the same stream."""
     C, T, D, fs = 6, 127, 100, 2400000
     n = 50000
@@ -79,12 +90,13 @@ def test_chunked_equals_one_shot(oracle):
     offs = synth.channel_offsets(C, fs)
     exp_pcm, exp_iq = oracle_bank(oracle, lpf, offs, fs, D, iq)
     for chunks in ([4096] * 13, [1, 50, 126, 127, 128, 4096, 9999, 3, 100000], [7777] * 7):
-        pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq, chunks=chunks, max_batch=100000)
+        pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq, chunks=chunks, max_batch=100000, engine=engine)
         assert_same(pcm, yiq, exp_pcm[:, :pcm.shape[1]], exp_iq[:, :pcm.shape[1]])
         assert pcm.shape[1] == exp_pcm.shape[1]
 
 
-def test_full_scale_and_gain_wraparound(oracle):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_full_scale_and_gain_wraparound(oracle, engine):
     """int32 accumulators wrap, int16 truncation after rq: full-scale input with a +6 'dB' gain."""
     C, T, D, fs = 4, 127, 50, 2400000
     n = 20000
@@ -93,22 +105,24 @@ def test_full_scale_and_gain_wraparound(oracle):
     lpf = synth.lowpass_taps(T, 200000.0, fs)
     offs = np.array([0, 600000, -600000, 1], dtype=np.int32)
     gains = np.array([1.0, 3.98, 15.0, 0.5])
-    pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq, gains=gains)
+    pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq, gains=gains, engine=engine)
     exp_pcm, exp_iq = oracle_bank(oracle, lpf, offs, fs, D, iq, gains=gains)
     assert_same(pcm, yiq, exp_pcm, exp_iq)
 
 
-def test_nofma_variant(oracle):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_nofma_variant(oracle, engine):
     C, T, D, fs = 3, 127, 100, 2400000
     iq = rand_iq(30000, seed=3)
     lpf = synth.lowpass_taps(T, 9000.0, fs)
     offs = synth.channel_offsets(C, fs)
-    pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq, flags=F_KEEP_IQ)
+    pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq, flags=F_KEEP_IQ, engine=engine)
     exp_pcm, exp_iq = oracle_bank(oracle, lpf, offs, fs, D, iq, fma=0)
     assert_same(pcm, yiq, exp_pcm, exp_iq)
 
 
-def test_long_stream_rot_limit_cycle(oracle):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_long_stream_rot_limit_cycle(oracle, engine):
     """Derotator transient -> limit cycle: the tabulated cycle must equal the recurrence
     after ~5e5 outputs; final rot compared with the oracle's state."""
     C, T, D, fs = 3, 16, 4, 2400000
@@ -116,7 +130,7 @@ def test_long_stream_rot_limit_cycle(oracle):
     iq = rand_iq(n, seed=9, amp=8000)
     lpf = synth.lowpass_taps(T, 100000.0, fs)
     offs = np.array([312500, -320000, 25000], dtype=np.int32)
-    pcm, yiq, state = run_bank(lpf, offs, fs, D, iq, chunks=[500000] * 5, flags=F_ATAN_FMA)
+    pcm, yiq, state = run_bank(lpf, offs, fs, D, iq, chunks=[500000] * 5, flags=F_ATAN_FMA, engine=engine)
     for c, off in enumerate(offs):
         re, im = oracle.prepare_taps(lpf, off, fs)
         st = oracle.new_state(off, fs, D)
@@ -138,17 +152,51 @@ def test_taps_match_oracle(oracle, pkg):
         assert np.array_equal(pkg.derot_increment(off, fs, 100), oracle.derot_incr(off, fs, 100))
 
 
-def test_against_reference_objects(ref, oracle):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_against_reference_objects(ref, oracle, engine):
     """Same input through the reference's own direct_fir + fm_demod (oracle/_ref) and the CUDA bank."""
     C, T, D, fs = 8, 127, 25, 1200000
     n = 4096 * 20
     iq = rand_iq(n, seed=21)
     lpf = synth.lowpass_taps(T, 9000.0, fs)
     offs = synth.channel_offsets(C, fs)
-    pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq)
+    pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq, engine=engine)
     for c, off in enumerate(offs):
         r_iq, r_pcm = ref.channel(lpf, off, fs, D, iq)
         k = len(r_pcm)
         assert k > 0 and k <= pcm.shape[1]
         assert np.array_equal(r_pcm, pcm[c, :k])
         assert np.array_equal(r_iq.reshape(-1, 2), yiq[c, :k])
+
+
+@pytest.mark.parametrize("C,T,D,fs,cut,gain", [
+    (64, 127, 100, 2400000, 9000.0, 1.0),       # benchmark shape
+    (64, 127, 100, 2400000, 4000.0, 1.0),       # narrow filter: every tap fits int8 -> single-limb path
+    (64, 127, 100, 2400000, 9000.0, 7.5),       # gain pushes taps into the two-limb path
+    (130, 127, 100, 2400000, 9000.0, 1.0),      # three channel groups, the last one partially filled
+    (256, 127, 25, 1200000, 9000.0, 2.0),       # Q = 6 block rows, odd decimation (row padding)
+    (64, 96, 96, 2400000, 20000.0, 3.0),        # Q = 1, Kp = 192
+    (40, 255, 200, 10000000, 9000.0, 1.0),      # long rows (Kp = 416)
+])
+def test_tensor_core_engine_shapes(oracle, C, T, D, fs, cut, gain):
+    n = 63 * D * 9 + T + 5 * D + 17             # several tiles, ragged last tile
+    iq = rand_iq(n, seed=C + T + D, amp=9000.0)
+    lpf = synth.lowpass_taps(T, cut, fs)
+    offs = synth.channel_offsets(C, fs)
+    gains = np.full(C, gain)
+    pcm, yiq, _ = run_bank(lpf, offs, fs, D, iq, gains=gains, engine=ENGINE_TC, chunks=[n // 3, n - n // 3], max_batch=n)
+    sel = sorted(set([0, 1, C // 2, C - 2, C - 1, 63 % C, 64 % C]))
+    for c in sel:
+        y, p = oracle.channel(lpf, offs[c], fs, D, iq, gain=gain)
+        assert pcm.shape[1] == len(p)
+        assert np.array_equal(yiq[c], y.reshape(-1, 2)), f"channel {c} IQ"
+        assert np.array_equal(pcm[c], p), f"channel {c} PCM"
+
+
+def test_auto_engine_picks_tensor_cores_for_wide_banks():
+    fs, T, D = 2400000, 127, 100
+    lpf = synth.lowpass_taps(T, 9000.0, fs)
+    a = GpuChan(lpf, synth.channel_offsets(64, fs), fs, D, 1 << 16)
+    b = GpuChan(lpf, synth.channel_offsets(3, fs), fs, D, 1 << 16)
+    assert a.engine == ENGINE_TC and b.engine == ENGINE_IMAD
+    a.close(); b.close()

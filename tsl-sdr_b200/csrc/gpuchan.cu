@@ -18,6 +18,7 @@
  */
 #include "../../include/tslb200_gpuchan.h"
 #include "fm_math.cuh"
+#include "tc_engine.cuh"
 
 #include <cuda_runtime.h>
 
@@ -107,20 +108,6 @@ constexpr int CTA_THREADS = (FIR_WARPS + 1) * 32;   /* + 1 warp expanding the de
 constexpr int ROT_LMAX    = 4096;    /* longest derotator limit cycle we tabulate */
 constexpr uint32_t ROT_BUDGET = 1u << 24;   /* cycle-detection step budget per channel */
 
-/* logical input stream of one submit = [carry | fresh]; out-of-range reads are zero */
-struct InWindow {
-    const int *carry;   /* packed (re | im << 16) */
-    const int *fresh;
-    long long carry_len;
-    long long total;    /* carry_len + fresh_len */
-};
-
-__device__ __forceinline__ int in_sample(const InWindow &w, long long s)
-{
-    if (s < 0 || s >= w.total) return 0;
-    return (s < w.carry_len) ? __ldg(w.carry + s) : __ldg(w.fresh + (s - w.carry_len));
-}
-
 /* -------------------------------------------------------------------------------------- */
 /* Derotator recurrence analysis: the map rot -> rq(rot*incr) acts on a finite set, so every
  * orbit is eventually periodic.  Brent's algorithm finds transient mu and period lambda. */
@@ -157,13 +144,22 @@ __global__ void rot_cycle_detect_kernel(const int *__restrict__ incr, int nr_cha
 }
 
 /* -------------------------------------------------------------------------------------- */
-/* Per submit: derotator phase at the first FIR output of every tile.
- * Tile t covers FIR outputs j = 0..KT-1 <-> stream output index g = k0 + t*KP - 1 + j (KP = KT-1);
- * j = 0 only feeds the discriminator's "previous sample".  ckpt[t][c] = rot at g(t, j = (t==0)). */
+/* Per submit: derotator phase checkpoints.  Tile t covers FIR outputs (columns) j = 0..KT-1 <-> stream output
+ * index k0 + t*KP - 1 + j (KP = KT-1); column 0 only feeds the discriminator's "previous sample".
+ * There are `sub` checkpoints per tile: r = 0 is the phase of column 0 (column 1 for the first tile of a
+ * submit, whose column 0 is the previous submit's last output), r > 0 the phase of column 16r-1.
+ * ckpt[(t*sub + r)*C + c]. */
+__device__ __forceinline__ unsigned long long ckpt_index(unsigned long long k0, int t, int r, int KP)
+{
+    const long long col = (r == 0) ? 0 : 16 * r - 1;
+    const long long g = (long long)k0 + (long long)t * KP + col - 1 + ((t == 0 && r == 0) ? 1 : 0);
+    return (unsigned long long)g;
+}
+
 __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict__ rot_state, int nr_channels,
                                    const uint32_t *__restrict__ mu, const uint32_t *__restrict__ lambda,
                                    const int *__restrict__ cyc, unsigned long long k0, unsigned long long K,
-                                   int KP, int nr_tiles, int *__restrict__ ckpt)
+                                   int KP, int sub, int nr_tiles, int *__restrict__ ckpt)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nr_channels) return;
@@ -183,39 +179,41 @@ __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict
         cur = g;
     };
 
-    for (int t = 0; t < nr_tiles; t++) {
-        const unsigned long long g = k0 + (unsigned long long)t * KP - (t > 0 ? 1 : 0);
-        seek(g);
-        ckpt[(size_t)t * nr_channels + c] = pack16(r_re, r_im);
-    }
+    for (int t = 0; t < nr_tiles; t++)
+        for (int r = 0; r < sub; r++) {
+            const unsigned long long g = ckpt_index(k0, t, r, KP);
+            if (g > k0 + K) continue;           /* past the last output of this submit: never read, and the
+                                                   sequential walk must not overshoot the state we hand on */
+            seek(g);
+            ckpt[((size_t)t * sub + r) * nr_channels + c] = pack16(r_re, r_im);
+        }
     seek(k0 + K);
     rot_state[c] = pack16(r_re, r_im);
 }
 
 /* Steady-state variant: every channel is past its transient (k0 >= mu) and has a tabulated cycle, so
- * each (tile, channel) checkpoint is an independent table lookup. */
+ * every checkpoint is an independent table lookup. */
 __global__ void rot_prepass_table_kernel(int *__restrict__ rot_state, int nr_channels, const uint32_t *__restrict__ mu,
                                          const uint32_t *__restrict__ lambda, const int *__restrict__ cyc,
-                                         unsigned long long k0, unsigned long long K, int KP, int nr_tiles,
+                                         unsigned long long k0, unsigned long long K, int KP, int sub, int nr_tiles,
                                          int *__restrict__ ckpt)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nr_channels) return;
     const uint32_t m = mu[c], lam = lambda[c];
     const int *tab = cyc + (size_t)c * ROT_LMAX;
-    /* phase of the first tile, then advance by KP (mod lambda) per tile: no 64-bit division in the loop */
     const int t_begin = blockIdx.y * 256;
     const int t_end = min(nr_tiles, t_begin + 256);
     if (t_begin >= nr_tiles) return;
-    const unsigned long long g0 = k0 + (unsigned long long)t_begin * KP - (t_begin > 0 ? 1 : 0);
-    uint32_t ph = (uint32_t)((g0 - m) % lam);
-    const uint32_t step = (uint32_t)(KP % (int)lam);
-    for (int t = t_begin; t < t_end; t++) {
-        ckpt[(size_t)t * nr_channels + c] = tab[ph];
-        uint32_t adv = step;
-        if (t == 0) adv = (uint32_t)((KP - 1) % (int)lam);      /* tile 0 has no leading output */
-        ph += adv; if (ph >= lam) ph -= lam;
-    }
+    unsigned long long prev = ckpt_index(k0, t_begin, 0, KP);
+    uint32_t ph = (uint32_t)((prev - m) % lam);             /* one 64-bit division per thread */
+    for (int t = t_begin; t < t_end; t++)
+        for (int r = 0; r < sub; r++) {
+            const unsigned long long g = ckpt_index(k0, t, r, KP);
+            ph = (ph + (uint32_t)(g - prev)) % lam;
+            prev = g;
+            ckpt[((size_t)t * sub + r) * nr_channels + c] = tab[ph];
+        }
     if (blockIdx.y == 0) rot_state[c] = tab[(k0 + K - m) % lam];
 }
 
@@ -422,6 +420,12 @@ struct gpuchan {
 
     /* kernel variant */
     int cpt = 2, R = 8;
+
+    /* tensor-core engine */
+    TcPlan tc;
+    uint8_t *d_tap_img = nullptr, *d_plane_hi = nullptr, *d_plane_lo = nullptr;
+    long long plane_rows = 0;
+    int nr_sms = 148;
 };
 
 static void host_atan_table(float2 *out)
@@ -446,7 +450,7 @@ static int free_all(gpuchan *h)
     cudaFree(h->d_last[0]); cudaFree(h->d_last[1]);
     cudaFree(h->d_mu); cudaFree(h->d_lambda); cudaFree(h->d_cyc);
     cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_ckpt);
-    cudaFree(h->d_atan);
+    cudaFree(h->d_atan); cudaFree(h->d_tap_img); cudaFree(h->d_plane_hi); cudaFree(h->d_plane_lo);
     for (int i = 0; i < gpuchan::NSLOT; i++) {
         cudaFree(h->d_stage[i]); cudaFree(h->d_pcm[i]); cudaFree(h->d_iq[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -495,6 +499,7 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
     h->Cpad = (h->C + 63) & ~63;
     h->fs = cfg->sample_rate_hz; h->flags = cfg->flags; h->max_batch = cfg->max_batch_samples;
     h->smem_max = (int)prop.sharedMemPerBlockOptin;
+    h->nr_sms = prop.multiProcessorCount;
     h->engine = GPUCHAN_ENGINE_IMAD;
 
 #define FAIL_TRY(expr)                                                                          \
@@ -525,19 +530,49 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
             packed[(size_t)i * Cpad + c] = ((int)h->h_re[(size_t)c * T + i] & 0xffff) | ((int)h->h_im[(size_t)c * T + i] << 16);
     }
 
-    /* --- pick the kernel variant that fits shared memory --- */
-    if      (C > 32 && variant_fits<2, 8>(h)) { h->cpt = 2; h->R = 8; }
-    else if (variant_fits<1, 8>(h) && C <= 32) { h->cpt = 1; h->R = 8; }
-    else if (C > 32 && variant_fits<2, 4>(h)) { h->cpt = 2; h->R = 4; }
-    else if (variant_fits<1, 8>(h))           { h->cpt = 1; h->R = 8; }
-    else if (variant_fits<1, 4>(h))           { h->cpt = 1; h->R = 4; }
-    else { free_all(h); return set_err(GPUCHAN_E_INVAL, "taps=%d decimation=%d do not fit shared memory", T, h->D); }
+    /* --- engine selection --- */
+    if (cfg->engine != GPUCHAN_ENGINE_AUTO && cfg->engine != GPUCHAN_ENGINE_IMAD && cfg->engine != GPUCHAN_ENGINE_TC) {
+        free_all(h);
+        return set_err(GPUCHAN_E_BADARGS, "unknown engine %u", cfg->engine);
+    }
+    if (cfg->engine == GPUCHAN_ENGINE_TC || (cfg->engine == GPUCHAN_ENGINE_AUTO && C >= 32)) {
+        h->tc = tc_make_plan(T, h->D, C, h->h_re.data(), h->h_im.data(), h->smem_max);
+        if (h->tc.ok) h->engine = GPUCHAN_ENGINE_TC;
+        else if (cfg->engine == GPUCHAN_ENGINE_TC) {
+            const char *why = h->tc.why;
+            free_all(h);
+            return set_err(GPUCHAN_E_INVAL, "tensor-core engine unavailable: %s", why);
+        }
+    }
 
-    const int KP = FIR_WARPS * h->R - 1;
+    /* --- pick the IMAD kernel variant that fits shared memory (also the fallback engine) --- */
+    if (h->engine == GPUCHAN_ENGINE_IMAD) {
+        if      (C > 32 && variant_fits<2, 8>(h)) { h->cpt = 2; h->R = 8; }
+        else if (variant_fits<1, 8>(h) && C <= 32) { h->cpt = 1; h->R = 8; }
+        else if (C > 32 && variant_fits<2, 4>(h)) { h->cpt = 2; h->R = 4; }
+        else if (variant_fits<1, 8>(h))           { h->cpt = 1; h->R = 8; }
+        else if (variant_fits<1, 4>(h))           { h->cpt = 1; h->R = 4; }
+        else { free_all(h); return set_err(GPUCHAN_E_INVAL, "taps=%d decimation=%d do not fit shared memory", T, h->D); }
+    }
+
+    const bool use_tc = h->engine == GPUCHAN_ENGINE_TC;
+    const int KP = use_tc ? TC_KP : FIR_WARPS * h->R - 1;
+    const int sub = use_tc ? TC_SUB : 1;
     const size_t max_avail = h->max_batch + (size_t)T;
     const size_t max_K = max_avail / h->D + 2;
     h->pitch = (max_K + 63) & ~(size_t)63;
     h->ckpt_tiles = (max_K + KP - 1) / KP + 1;
+
+    if (use_tc) {
+        std::vector<uint8_t> img;
+        tc_build_tap_image(h->tc, h->h_re.data(), h->h_im.data(), img);
+        FAIL_TRY(cudaMalloc(&h->d_tap_img, img.size()));
+        FAIL_TRY(cudaMemcpy(h->d_tap_img, img.data(), img.size(), cudaMemcpyHostToDevice));
+        h->plane_rows = (long long)h->ckpt_tiles * TC_KP + h->tc.Q + 72;
+        const size_t plane_bytes = (size_t)h->tc.Kp * h->plane_rows;
+        FAIL_TRY(cudaMalloc(&h->d_plane_hi, plane_bytes));
+        FAIL_TRY(cudaMalloc(&h->d_plane_lo, plane_bytes));
+    }
 
     FAIL_TRY(cudaMalloc(&h->d_taps, packed.size() * sizeof(int)));
     FAIL_TRY(cudaMemcpy(h->d_taps, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -554,7 +589,7 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
     FAIL_TRY(cudaMalloc(&h->d_mu, C * sizeof(uint32_t)));
     FAIL_TRY(cudaMalloc(&h->d_lambda, C * sizeof(uint32_t)));
     FAIL_TRY(cudaMalloc(&h->d_cyc, (size_t)C * ROT_LMAX * sizeof(int)));
-    FAIL_TRY(cudaMalloc(&h->d_ckpt, h->ckpt_tiles * C * sizeof(int)));
+    FAIL_TRY(cudaMalloc(&h->d_ckpt, h->ckpt_tiles * sub * C * sizeof(int)));
     FAIL_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     FAIL_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     for (int i = 0; i < gpuchan::NSLOT; i++) {
@@ -642,43 +677,64 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
     in.total = avail;
 
     if (K > 0) {
-        const int KP = FIR_WARPS * h->R - 1;
+        const bool use_tc = h->engine == GPUCHAN_ENGINE_TC;
+        const int KP = use_tc ? TC_KP : FIR_WARPS * h->R - 1;
+        const int sub = use_tc ? TC_SUB : 1;
         const int nr_tiles = (int)((K + KP - 1) / KP);
         if ((size_t)nr_tiles > h->ckpt_tiles || K > h->pitch) return set_err(GPUCHAN_E_INVAL, "internal capacity exceeded");
 
         if (h->all_cyclic && h->k_total >= h->mu_max + 1) {
             dim3 g((h->C + 63) / 64, (nr_tiles + 255) / 256);
-            rot_prepass_table_kernel<<<g, 64, 0, st>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, KP,
+            rot_prepass_table_kernel<<<g, 64, 0, st>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, KP, sub,
                                                        nr_tiles, h->d_ckpt);
         } else {
             rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, st>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
-                                                                h->k_total, K, KP, nr_tiles, h->d_ckpt);
+                                                                h->k_total, K, KP, sub, nr_tiles, h->d_ckpt);
         }
         h->launches++;
         CUDA_TRY(cudaGetLastError());
 
-        FirFmParams p;
-        p.in = in;
-        p.taps = h->d_taps; p.incr = h->d_incr; p.ckpt = h->d_ckpt;
-        p.last_in = h->d_last[h->pp_last]; p.last_out = h->d_last[h->pp_last ^ 1];
-        p.atan_tab = h->d_atan;
-        p.pcm = h->d_pcm[slot]; p.iq_out = h->d_iq[slot]; p.pitch = (long long)h->pitch;
-        p.K = K; p.T = T; p.D = D; p.C = h->C; p.Cpad = h->Cpad;
-        p.first_stream = (h->k_total == 0);
-        p.atan = h->atan;
-
         cudaEvent_t t0 = nullptr, t1 = nullptr;
-        if (h->timing) {
-            CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
-            CUDA_TRY(cudaEventRecord(t0, st));
+        if (use_tc) {
+            TcBatch tb;
+            tb.in = in;
+            tb.plane_hi = h->d_plane_hi; tb.plane_lo = h->d_plane_lo;
+            tb.Mrows = (long long)nr_tiles * TC_KP + h->tc.Q + 8;
+            if (tb.Mrows > h->plane_rows) return set_err(GPUCHAN_E_INVAL, "internal plane capacity exceeded");
+            tb.tap_img = h->d_tap_img; tb.incr = h->d_incr; tb.ckpt = h->d_ckpt;
+            tb.last_in = h->d_last[h->pp_last]; tb.last_out = h->d_last[h->pp_last ^ 1];
+            tb.atan_tab = h->d_atan; tb.pcm = h->d_pcm[slot]; tb.iq_out = h->d_iq[slot]; tb.pitch = (long long)h->pitch;
+            tb.K = K; tb.nr_tiles = nr_tiles; tb.atan = h->atan;
+            CUDA_TRY(tc_launch_deinterleave(h->tc, tb, st));
+            h->launches++;
+            if (h->timing) {
+                CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
+                CUDA_TRY(cudaEventRecord(t0, st));
+            }
+            CUDA_TRY(tc_launch_fir_fm(h->tc, tb, h->nr_sms, st));
+            h->launches++;
+        } else {
+            FirFmParams p;
+            p.in = in;
+            p.taps = h->d_taps; p.incr = h->d_incr; p.ckpt = h->d_ckpt;
+            p.last_in = h->d_last[h->pp_last]; p.last_out = h->d_last[h->pp_last ^ 1];
+            p.atan_tab = h->d_atan;
+            p.pcm = h->d_pcm[slot]; p.iq_out = h->d_iq[slot]; p.pitch = (long long)h->pitch;
+            p.K = K; p.T = T; p.D = D; p.C = h->C; p.Cpad = h->Cpad;
+            p.first_stream = (h->k_total == 0);
+            p.atan = h->atan;
+            if (h->timing) {
+                CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
+                CUDA_TRY(cudaEventRecord(t0, st));
+            }
+            cudaError_t e;
+            if      (h->cpt == 2 && h->R == 8) e = launch_imad<2, 8>(h, p, nr_tiles, st);
+            else if (h->cpt == 2 && h->R == 4) e = launch_imad<2, 4>(h, p, nr_tiles, st);
+            else if (h->cpt == 1 && h->R == 8) e = launch_imad<1, 8>(h, p, nr_tiles, st);
+            else                               e = launch_imad<1, 4>(h, p, nr_tiles, st);
+            h->launches++;
+            CUDA_TRY(e);
         }
-        cudaError_t e;
-        if      (h->cpt == 2 && h->R == 8) e = launch_imad<2, 8>(h, p, nr_tiles, st);
-        else if (h->cpt == 2 && h->R == 4) e = launch_imad<2, 4>(h, p, nr_tiles, st);
-        else if (h->cpt == 1 && h->R == 8) e = launch_imad<1, 8>(h, p, nr_tiles, st);
-        else                               e = launch_imad<1, 4>(h, p, nr_tiles, st);
-        h->launches++;
-        CUDA_TRY(e);
         if (h->timing) { CUDA_TRY(cudaEventRecord(t1, st)); h->timed.emplace_back(t0, t1); }
         h->pp_last ^= 1;
         h->k_total += K;
