@@ -202,8 +202,8 @@ __global__ void rot_prepass_table_kernel(int *__restrict__ rot_state, int nr_cha
     if (c >= nr_channels) return;
     const uint32_t m = mu[c], lam = lambda[c];
     const int *tab = cyc + (size_t)c * ROT_LMAX;
-    const int t_begin = blockIdx.y * 256;
-    const int t_end = min(nr_tiles, t_begin + 256);
+    const int t_begin = blockIdx.y * 16;
+    const int t_end = min(nr_tiles, t_begin + 16);
     if (t_begin >= nr_tiles) return;
     unsigned long long prev = ckpt_index(k0, t_begin, 0, KP);
     uint32_t ph = (uint32_t)((prev - m) % lam);             /* one 64-bit division per thread */
@@ -684,7 +684,7 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
         if ((size_t)nr_tiles > h->ckpt_tiles || K > h->pitch) return set_err(GPUCHAN_E_INVAL, "internal capacity exceeded");
 
         if (h->all_cyclic && h->k_total >= h->mu_max + 1) {
-            dim3 g((h->C + 63) / 64, (nr_tiles + 255) / 256);
+            dim3 g((h->C + 63) / 64, (nr_tiles + 15) / 16);
             rot_prepass_table_kernel<<<g, 64, 0, st>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, KP, sub,
                                                        nr_tiles, h->d_ckpt);
         } else {

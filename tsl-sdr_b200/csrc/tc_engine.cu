@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
 
     uint8_t *sA = smem;                                         /* [Q][LIMBS][nslab][128][16] */
     uint8_t *sB = smem + p.a_group_bytes;                       /* [2 stages][2 planes][nslab][R][16] */
+    int *accbuf = reinterpret_cast<int *>(sB + 2 * (size_t)p.b_stage_bytes);   /* [64 columns][128 rows] recombined accumulators */
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nslab = p.Kp >> 4, nchunk = p.Kp >> 5;
     const int g = blockIdx.x % p.G;                             /* channel group of this CTA */
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             int it = 0;
             for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
                 const int s = it & 1, ph = (it >> 1) & 1;
-                ptx::mbar_wait(&b_empty[s], ph ^ 1);
+                ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1);
                 ptx::mbar_arrive_expect_tx(&b_full[s], p.b_stage_bytes);
                 uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
                 const uint32_t slab_bytes = (uint32_t)p.R * 16;
@@ -141,8 +142,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             int it = 0;
             for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
                 const int s = it & 1, ph = (it >> 1) & 1;
-                ptx::mbar_wait(&b_full[s], ph);
-                ptx::mbar_wait(&t_empty[s], ph ^ 1);
+                ptx::mbar_wait_sleep(&b_full[s], ph);
+                ptx::mbar_wait_sleep(&t_empty[s], ph ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)s * 256;         /* slots: +0 (2^16), +64 (2^8), +128 (1) */
                 const uint32_t b_hi = ptx::smem_u32(sB + (size_t)s * p.b_stage_bytes);
@@ -172,19 +173,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             }
         }
     } else {
-        /* ================= epilogue: TMEM -> derotate -> discriminate -> PCM ================= */
+        /* ================= epilogue: TMEM -> smem -> derotate -> discriminate -> PCM ================= */
         const int e = warp - 2;
         const int slice = warp & 3;                 /* TMEM lanes 32*slice .. +31 are the only ones this warp may read */
-        const int half = e >> 2;                    /* which 32-column half of the tile */
-        const int is_im = lane & 1;                 /* even lane = re row, odd lane = im row of the same channel */
-        const int ch = 16 * slice + (lane >> 1);
+        const int half = e >> 2;                    /* which 32-column half of the tile this warp drains */
+        const int row = 32 * slice + lane;          /* accumulator row: 2*channel + (0 = re, 1 = im) */
+        const uint32_t lane_base = (uint32_t)(32 * slice) << 16;
+        /* compute mapping: consecutive lanes = consecutive channels (conflict-free smem reads) */
+        const int et = tid - 64;                    /* 0..255 */
+        const int ch = et & 63;
+        const int r = et >> 6;                      /* 16-column range this thread turns into PCM */
+        const int c0 = 16 * r;
         const int c = g * TC_CH + ch;
         const bool live = c < p.C;
-        const int r = 2 * half + is_im;             /* 16-column range this thread turns into PCM */
-        const int c0 = 16 * r;
         const int iw = live ? __ldg(p.incr + c) : 0;
         const int i_re = lo16(iw), i_im = hi16(iw);
-        const uint32_t lane_base = (uint32_t)(32 * slice) << 16;
+        const int2 *acc2 = reinterpret_cast<const int2 *>(accbuf);
 
         int it = 0;
         for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
@@ -192,85 +196,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             ptx::mbar_wait(&t_full[s], ph);
             ptx::tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)s * 256 + lane_base;
-            const int cw = 32 * half;               /* first column of this warp's half */
-
-            int vA[16], vB[16], vL = 0;
-            {
+            const int cw = 32 * half;
+            /* ---- phase 1: drain TMEM, recombine the limbs modulo 2^32, park in smem as [column][row] ---- */
+#pragma unroll
+            for (int chunk = 0; chunk < 2; chunk++) {
                 int hh[16], mid[16], ll[16];
-                if (LIMBS == 2) ptx::tmem_ld16(acc + 0 + cw, hh);
-                ptx::tmem_ld16(acc + 64 + cw, mid);
-                ptx::tmem_ld16(acc + 128 + cw, ll);
+                const int cc = cw + 16 * chunk;
+                if (LIMBS == 2) ptx::tmem_ld16(acc + 0 + cc, hh);
+                ptx::tmem_ld16(acc + 64 + cc, mid);
+                ptx::tmem_ld16(acc + 128 + cc, ll);
                 ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; i++) vA[i] = ll[i] + (mid[i] << 8) + (LIMBS == 2 ? (hh[i] << 16) : 0);
-                if (LIMBS == 2) ptx::tmem_ld16(acc + 0 + cw + 16, hh);
-                ptx::tmem_ld16(acc + 64 + cw + 16, mid);
-                ptx::tmem_ld16(acc + 128 + cw + 16, ll);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; i++) vB[i] = ll[i] + (mid[i] << 8) + (LIMBS == 2 ? (hh[i] << 16) : 0);
-                if (half > 0) {
-                    int h1 = 0, m1, l1;
-                    if (LIMBS == 2) ptx::tmem_ld1(acc + 0 + cw - 1, h1);
-                    ptx::tmem_ld1(acc + 64 + cw - 1, m1);
-                    ptx::tmem_ld1(acc + 128 + cw - 1, l1);
-                    ptx::tmem_ld_wait();
-                    vL = l1 + (m1 << 8) + (LIMBS == 2 ? (h1 << 16) : 0);
-                }
+                for (int i = 0; i < 16; i++)
+                    accbuf[(cc + i) * 128 + row] = ll[i] + (mid[i] << 8) + (LIMBS == 2 ? (hh[i] << 16) : 0);
             }
-            /* accumulators are in registers: hand the TMEM stage back to the MMA warp */
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&t_empty[s]);
+            if (lane == 0) ptx::mbar_arrive(&t_empty[s]);   /* TMEM stage is free again */
+            asm volatile("bar.sync 1, 256;" ::: "memory");   /* all 64 columns parked */
 
-            /* pair exchange: even lane keeps columns [cw, cw+16), odd lane keeps [cw+16, cw+32) */
-            int re[16], im[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int other = __shfl_xor_sync(0xffffffffu, is_im ? vA[i] : vB[i], 1);
-                re[i] = is_im ? other : vA[i];
-                im[i] = is_im ? vB[i] : other;
-            }
-            /* column c0-1 (previous output, feeds the discriminator): even lane: (own vL, partner's vL);
-             * odd lane: (partner's vA[15], own vA[15]) */
-            const int lead_other = __shfl_xor_sync(0xffffffffu, is_im ? vL : vA[15], 1);
-            const int lead_re = is_im ? lead_other : vL;
-            const int lead_im = is_im ? vA[15] : lead_other;
-
+            /* ---- phase 2: one channel x 16 columns per thread ---- */
             if (live) {
                 const int cwk = __ldg(p.ckpt + ((size_t)t * TC_SUB + r) * p.C + c);
                 int r_re = lo16(cwk), r_im = hi16(cwk);
                 int p_re, p_im;
-                int i_start = 0;
-                if (r > 0) {                        /* checkpoint is the phase of column c0-1 */
-                    derotate(rq14(lead_re), rq14(lead_im), r_re, r_im, p_re, p_im);
+                int col = c0;
+                if (r > 0 || t > 0) {
+                    /* previous output (column c0-1, or the tile's leading column 0): checkpoint is its phase */
+                    const int lead = (r > 0) ? c0 - 1 : 0;
+                    const int2 v = acc2[lead * 64 + ch];
+                    derotate(rq14(v.x), rq14(v.y), r_re, r_im, p_re, p_im);
                     rot_step(r_re, r_im, i_re, i_im);
-                } else if (t > 0) {                 /* column 0 is the tile's leading output; checkpoint is its phase */
-                    derotate(rq14(re[0]), rq14(im[0]), r_re, r_im, p_re, p_im);
-                    rot_step(r_re, r_im, i_re, i_im);
-                    i_start = 1;
-                } else {                            /* very first column of the submit: y[k0-1] is carried state */
+                    if (r == 0) col = 1;
+                } else {
+                    /* very first column of the submit: y[k0-1] is carried state, checkpoint is column 1's phase */
                     const int lw = __ldg(p.last_in + c);
                     p_re = lo16(lw); p_im = hi16(lw);
-                    i_start = 1;                    /* checkpoint is the phase of column 1 */
+                    col = 1;
                 }
-                const long long kbase = (long long)t * TC_KP + c0 - 1;     /* stream output index of column c0 */
                 short *out = p.pcm + (size_t)c * p.pitch;
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    if (i < i_start) continue;
-                    const long long k = kbase + i;
+                const long long kofs = (long long)t * TC_KP - 1;            /* stream output index of column 0 */
+#pragma unroll 4
+                for (; col < c0 + 16; col++) {
+                    const int2 v = acc2[col * 64 + ch];
                     int y_re, y_im;
-                    derotate(rq14(re[i]), rq14(im[i]), r_re, r_im, y_re, y_im);
+                    derotate(rq14(v.x), rq14(v.y), r_re, r_im, y_re, y_im);
                     rot_step(r_re, r_im, i_re, i_im);
+                    const long long k = kofs + col;
                     if ((unsigned long long)k < p.K) {
-                        out[k] = (short)fm_pcm(y_re, y_im, p_re, p_im, atan_s, p.atan);
+                        out[k] = (short)fm_pcm_bf(y_re, y_im, p_re, p_im, atan_s, p.atan);
                         if (p.iq_out) p.iq_out[(size_t)c * p.pitch + k] = pack16(y_re, y_im);
                         if ((unsigned long long)k == p.K - 1) p.last_out[c] = pack16(y_re, y_im);
                     }
                     p_re = y_re; p_im = y_im;
                 }
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   /* accbuf may be overwritten by the next tile */
         }
     }
 
@@ -314,7 +295,7 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
     pl.limbs = fits8 ? 1 : 2;
     pl.a_group_bytes = (size_t)pl.Q * pl.limbs * pl.Kp * 128;
     pl.b_stage_bytes = (size_t)2 * pl.Kp * pl.R;
-    pl.smem_bytes = pl.a_group_bytes + 2 * pl.b_stage_bytes + 128;
+    pl.smem_bytes = pl.a_group_bytes + 2 * pl.b_stage_bytes + (size_t)TC_N * 128 * 4 + 128;
     const size_t static_smem = 2048 + 256;
     if (pl.smem_bytes + static_smem > (size_t)smem_max) { pl.why = "tap image + sample ring exceed shared memory"; return pl; }
     if ((size_t)pl.R * 16 >= (1u << 18)) { pl.why = "tile too tall for the descriptor"; return pl; }

@@ -48,6 +48,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) { }
 }
+/* for the single-lane producer / MMA roles: do not burn issue slots the epilogue warps need */
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 
 /* ---- 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier ---- */
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
