@@ -147,11 +147,11 @@ __global__ void rot_cycle_detect_kernel(const int *__restrict__ incr, int nr_cha
 /* Per submit: derotator phase checkpoints.  Tile t covers FIR outputs (columns) j = 0..KT-1 <-> stream output
  * index k0 + t*KP - 1 + j (KP = KT-1); column 0 only feeds the discriminator's "previous sample".
  * There are `sub` checkpoints per tile: r = 0 is the phase of column 0 (column 1 for the first tile of a
- * submit, whose column 0 is the previous submit's last output), r > 0 the phase of column 16r-1.
+ * submit, whose column 0 is the previous submit's last output), r > 0 the phase of column step*r-1.
  * ckpt[(t*sub + r)*C + c]. */
-__device__ __forceinline__ unsigned long long ckpt_index(unsigned long long k0, int t, int r, int KP)
+__device__ __forceinline__ unsigned long long ckpt_index(unsigned long long k0, int t, int r, int KP, int step)
 {
-    const long long col = (r == 0) ? 0 : 16 * r - 1;
+    const long long col = (r == 0) ? 0 : step * r - 1;
     const long long g = (long long)k0 + (long long)t * KP + col - 1 + ((t == 0 && r == 0) ? 1 : 0);
     return (unsigned long long)g;
 }
@@ -159,7 +159,7 @@ __device__ __forceinline__ unsigned long long ckpt_index(unsigned long long k0, 
 __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict__ rot_state, int nr_channels,
                                    const uint32_t *__restrict__ mu, const uint32_t *__restrict__ lambda,
                                    const int *__restrict__ cyc, unsigned long long k0, unsigned long long K,
-                                   int KP, int sub, int nr_tiles, int *__restrict__ ckpt)
+                                   int KP, int sub, int step, int nr_tiles, int *__restrict__ ckpt)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nr_channels) return;
@@ -181,7 +181,7 @@ __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict
 
     for (int t = 0; t < nr_tiles; t++)
         for (int r = 0; r < sub; r++) {
-            const unsigned long long g = ckpt_index(k0, t, r, KP);
+            const unsigned long long g = ckpt_index(k0, t, r, KP, step);
             if (g > k0 + K) continue;           /* past the last output of this submit: never read, and the
                                                    sequential walk must not overshoot the state we hand on */
             seek(g);
@@ -195,8 +195,8 @@ __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict
  * every checkpoint is an independent table lookup. */
 __global__ void rot_prepass_table_kernel(int *__restrict__ rot_state, int nr_channels, const uint32_t *__restrict__ mu,
                                          const uint32_t *__restrict__ lambda, const int *__restrict__ cyc,
-                                         unsigned long long k0, unsigned long long K, int KP, int sub, int nr_tiles,
-                                         int *__restrict__ ckpt)
+                                         unsigned long long k0, unsigned long long K, int KP, int sub, int step,
+                                         int nr_tiles, int *__restrict__ ckpt)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nr_channels) return;
@@ -205,11 +205,11 @@ __global__ void rot_prepass_table_kernel(int *__restrict__ rot_state, int nr_cha
     const int t_begin = blockIdx.y * 16;
     const int t_end = min(nr_tiles, t_begin + 16);
     if (t_begin >= nr_tiles) return;
-    unsigned long long prev = ckpt_index(k0, t_begin, 0, KP);
+    unsigned long long prev = ckpt_index(k0, t_begin, 0, KP, step);
     uint32_t ph = (uint32_t)((prev - m) % lam);             /* one 64-bit division per thread */
     for (int t = t_begin; t < t_end; t++)
         for (int r = 0; r < sub; r++) {
-            const unsigned long long g = ckpt_index(k0, t, r, KP);
+            const unsigned long long g = ckpt_index(k0, t, r, KP, step);
             ph = (ph + (uint32_t)(g - prev)) % lam;
             prev = g;
             ckpt[((size_t)t * sub + r) * nr_channels + c] = tab[ph];
@@ -425,6 +425,7 @@ struct gpuchan {
     TcPlan tc;
     uint8_t *d_tap_img = nullptr, *d_plane_hi = nullptr, *d_plane_lo = nullptr;
     long long plane_rows = 0;
+    long long *d_dbg = nullptr;             /* role clock stamps (GPUCHAN_DEBUG_STAMPS=1) */
     int nr_sms = 148;
 };
 
@@ -450,7 +451,7 @@ static int free_all(gpuchan *h)
     cudaFree(h->d_last[0]); cudaFree(h->d_last[1]);
     cudaFree(h->d_mu); cudaFree(h->d_lambda); cudaFree(h->d_cyc);
     cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_ckpt);
-    cudaFree(h->d_atan); cudaFree(h->d_tap_img); cudaFree(h->d_plane_hi); cudaFree(h->d_plane_lo);
+    cudaFree(h->d_atan); cudaFree(h->d_tap_img); cudaFree(h->d_plane_hi); cudaFree(h->d_plane_lo); cudaFree(h->d_dbg);
     for (int i = 0; i < gpuchan::NSLOT; i++) {
         cudaFree(h->d_stage[i]); cudaFree(h->d_pcm[i]); cudaFree(h->d_iq[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -572,6 +573,10 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
         const size_t plane_bytes = (size_t)h->tc.Kp * h->plane_rows;
         FAIL_TRY(cudaMalloc(&h->d_plane_hi, plane_bytes));
         FAIL_TRY(cudaMalloc(&h->d_plane_lo, plane_bytes));
+        if (getenv("GPUCHAN_DEBUG_STAMPS")) {
+            FAIL_TRY(cudaMalloc(&h->d_dbg, 3 * 32 * 8 * sizeof(long long)));
+            FAIL_TRY(cudaMemset(h->d_dbg, 0, 3 * 32 * 8 * sizeof(long long)));
+        }
     }
 
     FAIL_TRY(cudaMalloc(&h->d_taps, packed.size() * sizeof(int)));
@@ -686,10 +691,10 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
         if (h->all_cyclic && h->k_total >= h->mu_max + 1) {
             dim3 g((h->C + 63) / 64, (nr_tiles + 15) / 16);
             rot_prepass_table_kernel<<<g, 64, 0, st>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, KP, sub,
-                                                       nr_tiles, h->d_ckpt);
+                                                       use_tc ? TC_STEP : 16, nr_tiles, h->d_ckpt);
         } else {
             rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, st>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
-                                                                h->k_total, K, KP, sub, nr_tiles, h->d_ckpt);
+                                                                h->k_total, K, KP, sub, use_tc ? TC_STEP : 16, nr_tiles, h->d_ckpt);
         }
         h->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -705,6 +710,7 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
             tb.last_in = h->d_last[h->pp_last]; tb.last_out = h->d_last[h->pp_last ^ 1];
             tb.atan_tab = h->d_atan; tb.pcm = h->d_pcm[slot]; tb.iq_out = h->d_iq[slot]; tb.pitch = (long long)h->pitch;
             tb.K = K; tb.nr_tiles = nr_tiles; tb.atan = h->atan;
+            tb.dbg = h->d_dbg;
             CUDA_TRY(tc_launch_deinterleave(h->tc, tb, st));
             h->launches++;
             if (h->timing) {
@@ -938,5 +944,17 @@ extern "C" int gpuchan_host_alloc(void **pp, size_t bytes)
 extern "C" int gpuchan_host_free(void *p)
 {
     if (p) CUDA_TRY(cudaFreeHost(p));
+    return GPUCHAN_OK;
+}
+
+/* Diagnostics: clock stamps of CTA 0's producer / MMA / epilogue roles for the first 32 tiles of the last launch
+ * (only when the bank was created with GPUCHAN_DEBUG_STAMPS set in the environment). out: [3][32][8] int64. */
+extern "C" int gpuchan_debug_stamps(gpuchan_t *h, long long *out)
+{
+    if (!h || !out) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    if (!h->d_dbg) return set_err(GPUCHAN_E_INVAL, "stamps not enabled");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out, h->d_dbg, 3 * 32 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return GPUCHAN_OK;
 }

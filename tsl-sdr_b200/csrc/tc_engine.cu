@@ -33,8 +33,10 @@ namespace tslb200 {
 
 namespace {
 
-constexpr int TC_THREADS = 32 * 10;     /* producer warp, MMA warp, 8 epilogue warps */
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;
+constexpr int TC_THREADS = 32 * (2 + EPI_WARPS);    /* producer warp, MMA warp, epilogue warps */
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
+constexpr int PCM_PITCH = 66;           /* int16 per column row: 64 channels + 2 pad -> 33 words, conflict-free both ways */
 
 /* ---------------------------------------------------------------------------------------------- */
 __global__ void tc_deinterleave_kernel(InWindow in, int D, int nslab, long long Mrows, uint8_t *__restrict__ plane_hi,
@@ -74,6 +76,7 @@ struct TcKernelParams {
     int nr_tiles, C, G, Kp, Q, R;
     uint32_t a_group_bytes, b_stage_bytes;
     AtanParams atan;
+    long long *dbg;         /* optional per-role clock stamps of CTA 0 (bench diagnostics) */
 };
 
 template <int LIMBS>
@@ -87,6 +90,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
     uint8_t *sA = smem;                                         /* [Q][LIMBS][nslab][128][16] */
     uint8_t *sB = smem + p.a_group_bytes;                       /* [2 stages][2 planes][nslab][R][16] */
     int *accbuf = reinterpret_cast<int *>(sB + 2 * (size_t)p.b_stage_bytes);   /* [64 columns][128 rows] recombined accumulators */
+    short *pcmbuf = reinterpret_cast<short *>(accbuf + TC_N * 128);             /* [64 columns][PCM_PITCH] int16 PCM of the tile */
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nslab = p.Kp >> 4, nchunk = p.Kp >> 5;
     const int g = blockIdx.x % p.G;                             /* channel group of this CTA */
@@ -112,6 +116,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+#define DBG(role, it, slot) do { if (p.dbg && blockIdx.x == 0 && (it) < 32) p.dbg[((role) * 32 + (it)) * 8 + (slot)] = clock64(); } while (0)
 
     if (warp == 0) {
         /* ================= producer: sample tiles -> smem ring ================= */
@@ -119,7 +124,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             int it = 0;
             for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
                 const int s = it & 1, ph = (it >> 1) & 1;
+                DBG(0, it, 0);
                 ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1);
+                DBG(0, it, 1);
                 ptx::mbar_arrive_expect_tx(&b_full[s], p.b_stage_bytes);
                 uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
                 const uint32_t slab_bytes = (uint32_t)p.R * 16;
@@ -128,6 +135,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
                     ptx::bulk_g2s(dst + (size_t)j * slab_bytes, p.plane_hi + ((size_t)j * p.Mrows + row0) * 16, slab_bytes, &b_full[s]);
                     ptx::bulk_g2s(dst + (size_t)(nslab + j) * slab_bytes, p.plane_lo + ((size_t)j * p.Mrows + row0) * 16, slab_bytes, &b_full[s]);
                 }
+                DBG(0, it, 2);
             }
         }
     } else if (warp == 1) {
@@ -142,8 +150,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             int it = 0;
             for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
                 const int s = it & 1, ph = (it >> 1) & 1;
+                DBG(1, it, 0);
                 ptx::mbar_wait_sleep(&b_full[s], ph);
+                DBG(1, it, 1);
                 ptx::mbar_wait_sleep(&t_empty[s], ph ^ 1);
+                DBG(1, it, 2);
                 ptx::tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)s * 256;         /* slots: +0 (2^16), +64 (2^8), +128 (1) */
                 const uint32_t b_hi = ptx::smem_u32(sB + (size_t)s * p.b_stage_bytes);
@@ -168,40 +179,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
                         }
                     }
                 }
+                DBG(1, it, 3);
                 ptx::mma_commit(&b_empty[s]);       /* smem stage may be refilled once these MMAs have read it */
                 ptx::mma_commit(&t_full[s]);        /* accumulators complete */
+                DBG(1, it, 4);
             }
         }
     } else {
         /* ================= epilogue: TMEM -> smem -> derotate -> discriminate -> PCM ================= */
         const int e = warp - 2;
         const int slice = warp & 3;                 /* TMEM lanes 32*slice .. +31 are the only ones this warp may read */
-        const int half = e >> 2;                    /* which 32-column half of the tile this warp drains */
+        const int quarter = e >> 2;                 /* which 16-column quarter of the tile this warp drains */
         const int row = 32 * slice + lane;          /* accumulator row: 2*channel + (0 = re, 1 = im) */
         const uint32_t lane_base = (uint32_t)(32 * slice) << 16;
         /* compute mapping: consecutive lanes = consecutive channels (conflict-free smem reads) */
-        const int et = tid - 64;                    /* 0..255 */
+        const int et = tid - 64;                    /* 0 .. EPI_THREADS-1 */
         const int ch = et & 63;
-        const int r = et >> 6;                      /* 16-column range this thread turns into PCM */
-        const int c0 = 16 * r;
+        const int r = et >> 6;                      /* TC_STEP-column range this thread turns into PCM */
+        const int c0 = TC_STEP * r;
         const int c = g * TC_CH + ch;
         const bool live = c < p.C;
         const int iw = live ? __ldg(p.incr + c) : 0;
         const int i_re = lo16(iw), i_im = hi16(iw);
         const int2 *acc2 = reinterpret_cast<const int2 *>(accbuf);
+        short *const out_c = p.pcm + (size_t)c * p.pitch;
+        int *const iq_c = p.iq_out ? p.iq_out + (size_t)c * p.pitch : nullptr;
+        const int K32 = (int)p.K;                   /* outputs per channel of one submit always fit 31 bits */
 
         int it = 0;
         for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
             const int s = it & 1, ph = (it >> 1) & 1;
+            if (tid == 64) DBG(2, it, 0);
             ptx::mbar_wait(&t_full[s], ph);
+            if (tid == 64) DBG(2, it, 1);
             ptx::tc_fence_after();
-            const uint32_t acc = tmem_base + (uint32_t)s * 256 + lane_base;
-            const int cw = 32 * half;
             /* ---- phase 1: drain TMEM, recombine the limbs modulo 2^32, park in smem as [column][row] ---- */
-#pragma unroll
-            for (int chunk = 0; chunk < 2; chunk++) {
+            {
+                const uint32_t acc = tmem_base + (uint32_t)s * 256 + lane_base;
                 int hh[16], mid[16], ll[16];
-                const int cc = cw + 16 * chunk;
+                const int cc = 16 * quarter;
                 if (LIMBS == 2) ptx::tmem_ld16(acc + 0 + cc, hh);
                 ptx::tmem_ld16(acc + 64 + cc, mid);
                 ptx::tmem_ld16(acc + 128 + cc, ll);
@@ -213,9 +229,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&t_empty[s]);   /* TMEM stage is free again */
-            asm volatile("bar.sync 1, 256;" ::: "memory");   /* all 64 columns parked */
+            if (tid == 64) DBG(2, it, 2);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      /* all 64 columns parked */
+            if (tid == 64) DBG(2, it, 3);
 
-            /* ---- phase 2: one channel x 16 columns per thread ---- */
+            /* ---- phase 2: one channel x TC_STEP columns per thread ---- */
             if (live) {
                 const int cwk = __ldg(p.ckpt + ((size_t)t * TC_SUB + r) * p.C + c);
                 int r_re = lo16(cwk), r_im = hi16(cwk);
@@ -234,24 +252,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
                     p_re = lo16(lw); p_im = hi16(lw);
                     col = 1;
                 }
-                short *out = p.pcm + (size_t)c * p.pitch;
-                const long long kofs = (long long)t * TC_KP - 1;            /* stream output index of column 0 */
+                const int kofs = t * TC_KP - 1;                         /* stream output index of column 0 */
+                int col_end = c0 + TC_STEP;
+                if (kofs + col_end > K32) col_end = K32 - kofs;         /* ragged last tile */
+                const bool produced = col < col_end;
+                const int2 *src = acc2 + col * 64 + ch;
+                short *out = pcmbuf + col * PCM_PITCH + ch;
 #pragma unroll 4
-                for (; col < c0 + 16; col++) {
-                    const int2 v = acc2[col * 64 + ch];
+                for (; col < col_end; col++, src += 64, out += PCM_PITCH) {
+                    const int2 v = *src;
                     int y_re, y_im;
                     derotate(rq14(v.x), rq14(v.y), r_re, r_im, y_re, y_im);
                     rot_step(r_re, r_im, i_re, i_im);
-                    const long long k = kofs + col;
-                    if ((unsigned long long)k < p.K) {
-                        out[k] = (short)fm_pcm_bf(y_re, y_im, p_re, p_im, atan_s, p.atan);
-                        if (p.iq_out) p.iq_out[(size_t)c * p.pitch + k] = pack16(y_re, y_im);
-                        if ((unsigned long long)k == p.K - 1) p.last_out[c] = pack16(y_re, y_im);
-                    }
+                    *out = (short)fm_pcm_bf(y_re, y_im, p_re, p_im, atan_s, p.atan);
+                    if (iq_c) iq_c[kofs + col] = pack16(y_re, y_im);
                     p_re = y_re; p_im = y_im;
                 }
+                /* the thread that produced the submit's last output hands y[K-1] to the next submit */
+                if (produced && kofs + col_end == K32) p.last_out[c] = pack16(p_re, p_im);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");   /* accbuf may be overwritten by the next tile */
+            if (tid == 64) DBG(2, it, 4);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      /* accbuf free; the tile's PCM is complete in smem */
+            if (tid == 64) DBG(2, it, 5);
+            /* ---- phase 3: coalesced copy-out, lanes along time: each warp row = 32 consecutive int16 of one channel ---- */
+            {
+                const int kofs = t * TC_KP - 1;
+                int ncol = K32 - kofs;                                  /* valid columns are 1 .. ncol-1 */
+                if (ncol > TC_N) ncol = TC_N;
+                for (int idx = et; idx < TC_CH * TC_N; idx += EPI_THREADS) {
+                    const int chn = idx >> 6, colx = idx & 63;
+                    const int cg = g * TC_CH + chn;
+                    if (colx >= 1 && colx < ncol && cg < p.C)
+                        p.pcm[(size_t)cg * p.pitch + kofs + colx] = pcmbuf[colx * PCM_PITCH + chn];
+                }
+            }
         }
     }
 
@@ -295,7 +329,7 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
     pl.limbs = fits8 ? 1 : 2;
     pl.a_group_bytes = (size_t)pl.Q * pl.limbs * pl.Kp * 128;
     pl.b_stage_bytes = (size_t)2 * pl.Kp * pl.R;
-    pl.smem_bytes = pl.a_group_bytes + 2 * pl.b_stage_bytes + (size_t)TC_N * 128 * 4 + 128;
+    pl.smem_bytes = pl.a_group_bytes + 2 * pl.b_stage_bytes + (size_t)TC_N * 128 * 4 + (size_t)TC_N * 66 * 2 + 128;
     const size_t static_smem = 2048 + 256;
     if (pl.smem_bytes + static_smem > (size_t)smem_max) { pl.why = "tap image + sample ring exceed shared memory"; return pl; }
     if ((size_t)pl.R * 16 >= (1u << 18)) { pl.why = "tile too tall for the descriptor"; return pl; }
@@ -343,6 +377,7 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, int nr_sms, cud
     p.nr_tiles = b.nr_tiles; p.C = pl.C; p.G = pl.G; p.Kp = pl.Kp; p.Q = pl.Q; p.R = pl.R;
     p.a_group_bytes = (uint32_t)pl.a_group_bytes; p.b_stage_bytes = (uint32_t)pl.b_stage_bytes;
     p.atan = b.atan;
+    p.dbg = b.dbg;
     /* persistent grid: a multiple of G CTAs, at most one per SM, no more CTAs than (group, tile) pairs */
     long long ctas = (long long)(nr_sms / pl.G) * pl.G;
     if (ctas < pl.G) ctas = pl.G;

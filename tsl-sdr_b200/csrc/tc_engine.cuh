@@ -10,7 +10,8 @@ namespace tslb200 {
 
 constexpr int TC_N  = 64;               /* FIR outputs (columns) per tile: 1 leading + 63 PCM outputs */
 constexpr int TC_KP = TC_N - 1;         /* PCM outputs per tile */
-constexpr int TC_SUB = 4;               /* derotator checkpoints per tile (one per 16 columns) */
+constexpr int TC_STEP = 8;              /* columns one epilogue thread turns into PCM */
+constexpr int TC_SUB = TC_N / TC_STEP;  /* derotator checkpoints per tile (one per TC_STEP columns) */
 constexpr int TC_CH = 64;               /* channels per CTA (128 accumulator rows: re/im interleaved) */
 
 struct TcPlan {
@@ -45,6 +46,7 @@ struct TcBatch {
     unsigned long long K;
     int nr_tiles;
     AtanParams atan;
+    long long *dbg = nullptr;
 };
 
 cudaError_t tc_launch_deinterleave(const TcPlan &pl, const TcBatch &b, cudaStream_t st);
