@@ -260,6 +260,7 @@ def main():
     k_out = 0
     for i in range(args.steps):
         k_out += step_resident(args.warmup + i)
+    bank.stream_wait(sptr)                              # the bank works on its own streams: order ours after it
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)

@@ -83,10 +83,13 @@ int gpuchan_destroy(gpuchan_t **ph);
  * only if it is pageable (pinned buffers must stay untouched until gpuchan_sync/collect). */
 int gpuchan_submit(gpuchan_t *h, const int16_t *iq_host, size_t n_complex);
 
-/* Same, with the samples already resident on h's device (e.g. after an NCCL broadcast).  Work is
- * enqueued on cuda_stream (a cudaStream_t, NULL = the bank's own stream); d_iq must stay valid and
- * unmodified until that stream reaches this point. */
+/* Same, with the samples already resident on h's device (e.g. after an NCCL broadcast).  cuda_stream
+ * (a cudaStream_t) only tells WHEN d_iq becomes readable: the bank waits for that stream's current position and
+ * then works on its own streams, so the producer of batch i+1 overlaps the kernels of batch i.  NULL = readable
+ * now.  d_iq must stay unmodified until the batch has been collected / discarded or gpuchan_sync returned. */
 int gpuchan_submit_device(gpuchan_t *h, const int16_t *d_iq, size_t n_complex, void *cuda_stream);
+/* Order cuda_stream after everything submitted so far (event timing, chaining consumers on a caller stream). */
+int gpuchan_stream_wait(gpuchan_t *h, void *cuda_stream);
 
 /* Wait for all submitted work. */
 int gpuchan_sync(gpuchan_t *h);

@@ -423,7 +423,11 @@ struct gpuchan {
 
     /* tensor-core engine */
     TcPlan tc;
-    uint8_t *d_tap_img = nullptr, *d_plane_hi = nullptr, *d_plane_lo = nullptr;
+    uint8_t *d_tap_img = nullptr, *d_plane_hi[2] = { nullptr, nullptr }, *d_plane_lo[2] = { nullptr, nullptr };
+    int *d_ckpt2 = nullptr;                 /* second checkpoint buffer (pre-stream runs one batch ahead) */
+    cudaStream_t s_pre = nullptr;           /* prepass + carry + deinterleave of batch i+1 overlap the FIR/FM kernel of batch i */
+    cudaEvent_t ev_in = nullptr, ev_pre_done[2] = { nullptr, nullptr }, ev_main_done[2] = { nullptr, nullptr };
+    uint64_t tc_seq = 0;
     long long plane_rows = 0;
     long long *d_dbg = nullptr;             /* role clock stamps (GPUCHAN_DEBUG_STAMPS=1) */
     int nr_sms = 148;
@@ -451,7 +455,14 @@ static int free_all(gpuchan *h)
     cudaFree(h->d_last[0]); cudaFree(h->d_last[1]);
     cudaFree(h->d_mu); cudaFree(h->d_lambda); cudaFree(h->d_cyc);
     cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_ckpt);
-    cudaFree(h->d_atan); cudaFree(h->d_tap_img); cudaFree(h->d_plane_hi); cudaFree(h->d_plane_lo); cudaFree(h->d_dbg);
+    cudaFree(h->d_atan); cudaFree(h->d_tap_img); cudaFree(h->d_dbg); cudaFree(h->d_ckpt2);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(h->d_plane_hi[i]); cudaFree(h->d_plane_lo[i]);
+        if (h->ev_pre_done[i]) cudaEventDestroy(h->ev_pre_done[i]);
+        if (h->ev_main_done[i]) cudaEventDestroy(h->ev_main_done[i]);
+    }
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->s_pre) cudaStreamDestroy(h->s_pre);
     for (int i = 0; i < gpuchan::NSLOT; i++) {
         cudaFree(h->d_stage[i]); cudaFree(h->d_pcm[i]); cudaFree(h->d_iq[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -571,8 +582,14 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
         FAIL_TRY(cudaMemcpy(h->d_tap_img, img.data(), img.size(), cudaMemcpyHostToDevice));
         h->plane_rows = (long long)h->ckpt_tiles * TC_KP + h->tc.Q + 72;
         const size_t plane_bytes = (size_t)h->tc.Kp * h->plane_rows;
-        FAIL_TRY(cudaMalloc(&h->d_plane_hi, plane_bytes));
-        FAIL_TRY(cudaMalloc(&h->d_plane_lo, plane_bytes));
+        FAIL_TRY(cudaStreamCreateWithFlags(&h->s_pre, cudaStreamNonBlocking));
+        FAIL_TRY(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) {
+            FAIL_TRY(cudaMalloc(&h->d_plane_hi[i], plane_bytes));
+            FAIL_TRY(cudaMalloc(&h->d_plane_lo[i], plane_bytes));
+            FAIL_TRY(cudaEventCreateWithFlags(&h->ev_pre_done[i], cudaEventDisableTiming));
+            FAIL_TRY(cudaEventCreateWithFlags(&h->ev_main_done[i], cudaEventDisableTiming));
+        }
         if (getenv("GPUCHAN_DEBUG_STAMPS")) {
             FAIL_TRY(cudaMalloc(&h->d_dbg, 3 * 32 * 8 * sizeof(long long)));
             FAIL_TRY(cudaMemset(h->d_dbg, 0, 3 * 32 * 8 * sizeof(long long)));
@@ -595,6 +612,7 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
     FAIL_TRY(cudaMalloc(&h->d_lambda, C * sizeof(uint32_t)));
     FAIL_TRY(cudaMalloc(&h->d_cyc, (size_t)C * ROT_LMAX * sizeof(int)));
     FAIL_TRY(cudaMalloc(&h->d_ckpt, h->ckpt_tiles * sub * C * sizeof(int)));
+    if (use_tc) FAIL_TRY(cudaMalloc(&h->d_ckpt2, h->ckpt_tiles * sub * C * sizeof(int)));
     FAIL_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     FAIL_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     for (int i = 0; i < gpuchan::NSLOT; i++) {
@@ -638,11 +656,14 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
     return GPUCHAN_OK;
 }
 
+extern "C" int gpuchan_sync(gpuchan_t *h);
+
 extern "C" int gpuchan_destroy(gpuchan_t **ph)
 {
     if (!ph || !*ph) return set_err(GPUCHAN_E_BADARGS, "null handle");
     cudaSetDevice((*ph)->device);
-    cudaStreamSynchronize((*ph)->stream);
+    gpuchan_sync(*ph);
+    cudaDeviceSynchronize();
     free_all(*ph);
     *ph = nullptr;
     return GPUCHAN_OK;
@@ -668,12 +689,14 @@ static int slot_acquire(gpuchan *h)
     return GPUCHAN_OK;
 }
 
-/* enqueue all kernels of one submit on stream st; outputs land in slot */
-static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStream_t st, int slot)
+/* enqueue all kernels of one submit; the FIR/FM kernel runs on stream st, outputs land in slot.
+ * in_ready: event after which the fresh samples are readable (nullptr: already ordered on st). */
+static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStream_t st, int slot, cudaEvent_t in_ready)
 {
     const long long avail = h->carry_len + (long long)n_complex;
     const int T = h->T, D = h->D;
     const unsigned long long K = (avail >= T) ? (unsigned long long)((avail - T) / D + 1) : 0;
+    const bool use_tc = h->engine == GPUCHAN_ENGINE_TC;
 
     InWindow in;
     in.carry = h->d_carry[h->pp_carry];
@@ -681,58 +704,91 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
     in.carry_len = h->carry_len;
     in.total = avail;
 
-    if (K > 0) {
-        const bool use_tc = h->engine == GPUCHAN_ENGINE_TC;
-        const int KP = use_tc ? TC_KP : FIR_WARPS * h->R - 1;
-        const int sub = use_tc ? TC_SUB : 1;
-        const int nr_tiles = (int)((K + KP - 1) / KP);
-        if ((size_t)nr_tiles > h->ckpt_tiles || K > h->pitch) return set_err(GPUCHAN_E_INVAL, "internal capacity exceeded");
+    /* The tensor-core engine reads only the byte planes, so everything that touches the raw samples (derotator
+     * checkpoints, carry, deinterleave) runs on a second stream one batch ahead of the FIR/FM kernel. */
+    /* Measured on B200: next to the persistent FIR/FM kernel (1 CTA/SM, 213 KB smem) the pre-kernels only get
+     * ~2 CTAs per SM and become the critical path (step 0.29 -> 0.38 ms), so the second stream stays off. */
+    const bool overlap_pre = false;
+    cudaStream_t pre = (use_tc && overlap_pre) ? h->s_pre : st;
+    const int pb = (int)(h->tc_seq & 1);
+    if (pre != st) {
+        if (in_ready) CUDA_TRY(cudaStreamWaitEvent(pre, in_ready, 0));
+        CUDA_TRY(cudaStreamWaitEvent(pre, h->ev_main_done[pb], 0));     /* planes/checkpoints pb were read two batches ago */
+    } else if (in_ready) {
+        CUDA_TRY(cudaStreamWaitEvent(st, in_ready, 0));
+    }
+    int *ckpt = (use_tc && pb) ? h->d_ckpt2 : h->d_ckpt;
 
+    const int KP = use_tc ? TC_KP : FIR_WARPS * h->R - 1;
+    const int sub = use_tc ? TC_SUB : 1;
+    const int nr_tiles = (int)((K + KP - 1) / KP);
+    if (K > 0) {
+        if ((size_t)nr_tiles > h->ckpt_tiles || K > h->pitch) return set_err(GPUCHAN_E_INVAL, "internal capacity exceeded");
         if (h->all_cyclic && h->k_total >= h->mu_max + 1) {
             dim3 g((h->C + 63) / 64, (nr_tiles + 15) / 16);
-            rot_prepass_table_kernel<<<g, 64, 0, st>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, KP, sub,
-                                                       use_tc ? TC_STEP : 16, nr_tiles, h->d_ckpt);
+            rot_prepass_table_kernel<<<g, 64, 0, pre>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, KP, sub,
+                                                        use_tc ? TC_STEP : 16, nr_tiles, ckpt);
         } else {
-            rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, st>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
-                                                                h->k_total, K, KP, sub, use_tc ? TC_STEP : 16, nr_tiles, h->d_ckpt);
+            rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, pre>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
+                                                                 h->k_total, K, KP, sub, use_tc ? TC_STEP : 16, nr_tiles, ckpt);
         }
         h->launches++;
         CUDA_TRY(cudaGetLastError());
+    }
 
+    TcBatch tb;
+    if (use_tc && K > 0) {
+        tb.in = in;
+        tb.plane_hi = h->d_plane_hi[pb]; tb.plane_lo = h->d_plane_lo[pb];
+        tb.Mrows = (long long)nr_tiles * TC_KP + h->tc.Q + 8;
+        if (tb.Mrows > h->plane_rows) return set_err(GPUCHAN_E_INVAL, "internal plane capacity exceeded");
+        CUDA_TRY(tc_launch_deinterleave(h->tc, tb, pre));
+        h->launches++;
+    }
+
+    /* keep what the next submit still needs: samples [K*D, avail).  (IMAD engine: after the FIR kernel, see below) */
+    const long long from = (long long)K * D;
+    const long long keep = avail - from;     /* < T */
+    auto save_carry = [&](cudaStream_t s2) -> int {
+        if (keep > 0) {
+            carry_save_kernel<<<(unsigned)((keep + 255) / 256), 256, 0, s2>>>(in, from, h->d_carry[h->pp_carry ^ 1], (int)keep);
+            h->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        return GPUCHAN_OK;
+    };
+    if (use_tc) {
+        if (int rc = save_carry(pre)) return rc;
+        if (pre != st) {
+            CUDA_TRY(cudaEventRecord(h->ev_pre_done[pb], pre));
+            CUDA_TRY(cudaStreamWaitEvent(st, h->ev_pre_done[pb], 0));
+        }
+    }
+
+    if (K > 0) {
         cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (h->timing) {
+            CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
+            CUDA_TRY(cudaEventRecord(t0, st));
+        }
         if (use_tc) {
-            TcBatch tb;
-            tb.in = in;
-            tb.plane_hi = h->d_plane_hi; tb.plane_lo = h->d_plane_lo;
-            tb.Mrows = (long long)nr_tiles * TC_KP + h->tc.Q + 8;
-            if (tb.Mrows > h->plane_rows) return set_err(GPUCHAN_E_INVAL, "internal plane capacity exceeded");
-            tb.tap_img = h->d_tap_img; tb.incr = h->d_incr; tb.ckpt = h->d_ckpt;
+            tb.tap_img = h->d_tap_img; tb.incr = h->d_incr; tb.ckpt = ckpt;
             tb.last_in = h->d_last[h->pp_last]; tb.last_out = h->d_last[h->pp_last ^ 1];
             tb.atan_tab = h->d_atan; tb.pcm = h->d_pcm[slot]; tb.iq_out = h->d_iq[slot]; tb.pitch = (long long)h->pitch;
             tb.K = K; tb.nr_tiles = nr_tiles; tb.atan = h->atan;
             tb.dbg = h->d_dbg;
-            CUDA_TRY(tc_launch_deinterleave(h->tc, tb, st));
-            h->launches++;
-            if (h->timing) {
-                CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
-                CUDA_TRY(cudaEventRecord(t0, st));
-            }
             CUDA_TRY(tc_launch_fir_fm(h->tc, tb, h->nr_sms, st));
             h->launches++;
         } else {
             FirFmParams p;
             p.in = in;
-            p.taps = h->d_taps; p.incr = h->d_incr; p.ckpt = h->d_ckpt;
+            p.taps = h->d_taps; p.incr = h->d_incr; p.ckpt = ckpt;
             p.last_in = h->d_last[h->pp_last]; p.last_out = h->d_last[h->pp_last ^ 1];
             p.atan_tab = h->d_atan;
             p.pcm = h->d_pcm[slot]; p.iq_out = h->d_iq[slot]; p.pitch = (long long)h->pitch;
             p.K = K; p.T = T; p.D = D; p.C = h->C; p.Cpad = h->Cpad;
             p.first_stream = (h->k_total == 0);
             p.atan = h->atan;
-            if (h->timing) {
-                CUDA_TRY(cudaEventCreate(&t0)); CUDA_TRY(cudaEventCreate(&t1));
-                CUDA_TRY(cudaEventRecord(t0, st));
-            }
             cudaError_t e;
             if      (h->cpt == 2 && h->R == 8) e = launch_imad<2, 8>(h, p, nr_tiles, st);
             else if (h->cpt == 2 && h->R == 4) e = launch_imad<2, 4>(h, p, nr_tiles, st);
@@ -745,14 +801,11 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
         h->pp_last ^= 1;
         h->k_total += K;
     }
-
-    /* keep what the next submit still needs: samples [K*D, avail) */
-    const long long from = (long long)K * D;
-    const long long keep = avail - from;     /* < T */
-    if (keep > 0) {
-        carry_save_kernel<<<(unsigned)((keep + 255) / 256), 256, 0, st>>>(in, from, h->d_carry[h->pp_carry ^ 1], (int)keep);
-        h->launches++;
-        CUDA_TRY(cudaGetLastError());
+    if (use_tc) {
+        CUDA_TRY(cudaEventRecord(h->ev_main_done[pb], st));
+        h->tc_seq++;
+    } else {
+        if (int rc = save_carry(st)) return rc;
     }
     h->pp_carry ^= 1;
     h->carry_len = keep > 0 ? keep : 0;
@@ -769,17 +822,25 @@ extern "C" int gpuchan_submit_device(gpuchan_t *h, const int16_t *d_iq, size_t n
     if (n_complex > h->max_batch) return set_err(GPUCHAN_E_INVAL, "submit of %zu samples exceeds max_batch_samples %zu", n_complex, h->max_batch);
     if (int rc = slot_acquire(h)) return rc;
     CUDA_TRY(cudaSetDevice(h->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-    if (st != h->stream) {      /* order the caller's stream after everything already queued on ours */
-        CUDA_TRY(cudaEventRecord(h->ev_own, h->stream));
-        CUDA_TRY(cudaStreamWaitEvent(st, h->ev_own, 0));
+    /* cuda_stream only says WHEN the samples are readable; the bank always works on its own streams, so a
+     * producer stream (NCCL broadcast, H2D copy) can run ahead of the FIR/FM kernel of the previous batch. */
+    cudaEvent_t in_ready = nullptr;
+    if (cuda_stream) {
+        CUDA_TRY(cudaEventRecord(h->ev_ext, (cudaStream_t)cuda_stream));
+        in_ready = h->ev_ext;
     }
     const int slot = (int)(h->submit_seq % gpuchan::NSLOT);
-    if (int rc = run_batch(h, reinterpret_cast<const int *>(d_iq), n_complex, st, slot)) return rc;
-    if (st != h->stream) {      /* ... and our stream (next host submit) after the caller's */
-        CUDA_TRY(cudaEventRecord(h->ev_ext, st));
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_ext, 0));
-    }
+    return run_batch(h, reinterpret_cast<const int *>(d_iq), n_complex, h->stream, slot, in_ready);
+}
+
+/* Make cuda_stream wait for everything submitted to the bank so far (for callers that time or chain work on
+ * their own stream). */
+extern "C" int gpuchan_stream_wait(gpuchan_t *h, void *cuda_stream)
+{
+    if (!h || !cuda_stream) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventRecord(h->ev_own, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)cuda_stream, h->ev_own, 0));
     return GPUCHAN_OK;
 }
 
@@ -795,8 +856,7 @@ extern "C" int gpuchan_submit(gpuchan_t *h, const int16_t *iq_host, size_t n_com
     CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));
     if (n_complex) CUDA_TRY(cudaMemcpyAsync(h->d_stage[slot], iq_host, n_complex * 4, cudaMemcpyHostToDevice, h->s_in));
     CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
-    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
-    return run_batch(h, h->d_stage[slot], n_complex, h->stream, slot);
+    return run_batch(h, h->d_stage[slot], n_complex, h->stream, slot, h->ev_h2d[slot]);
 }
 
 extern "C" int gpuchan_sync(gpuchan_t *h)
@@ -805,6 +865,7 @@ extern "C" int gpuchan_sync(gpuchan_t *h)
     CUDA_TRY(cudaSetDevice(h->device));
     for (int i = 0; i < gpuchan::NSLOT; i++) CUDA_TRY(cudaEventSynchronize(h->ev_done[i]));
     CUDA_TRY(cudaStreamSynchronize(h->s_in));
+    if (h->s_pre) CUDA_TRY(cudaStreamSynchronize(h->s_pre));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->s_out));
     return GPUCHAN_OK;
@@ -888,8 +949,7 @@ extern "C" int gpuchan_get_rot_state(gpuchan_t *h, uint32_t channel, int16_t rot
                                      uint64_t *outputs_so_far, uint32_t *cycle_mu, uint32_t *cycle_lambda)
 {
     if (!h || channel >= (uint32_t)h->C) return set_err(GPUCHAN_E_BADARGS, "bad argument");
-    CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (int rc = gpuchan_sync(h)) return rc;
     int w = 0;
     uint32_t mu = 0, lam = 0;
     CUDA_TRY(cudaMemcpy(&w, h->d_rot + channel, sizeof(int), cudaMemcpyDeviceToHost));

@@ -202,7 +202,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
         const int iw = live ? __ldg(p.incr + c) : 0;
         const int i_re = lo16(iw), i_im = hi16(iw);
         const int2 *acc2 = reinterpret_cast<const int2 *>(accbuf);
-        short *const out_c = p.pcm + (size_t)c * p.pitch;
         int *const iq_c = p.iq_out ? p.iq_out + (size_t)c * p.pitch : nullptr;
         const int K32 = (int)p.K;                   /* outputs per channel of one submit always fit 31 bits */
 
@@ -258,7 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
                 const bool produced = col < col_end;
                 const int2 *src = acc2 + col * 64 + ch;
                 short *out = pcmbuf + col * PCM_PITCH + ch;
-#pragma unroll 4
+#pragma unroll 8
                 for (; col < col_end; col++, src += 64, out += PCM_PITCH) {
                     const int2 v = *src;
                     int y_re, y_im;
@@ -274,16 +273,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             if (tid == 64) DBG(2, it, 4);
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      /* accbuf free; the tile's PCM is complete in smem */
             if (tid == 64) DBG(2, it, 5);
-            /* ---- phase 3: coalesced copy-out, lanes along time: each warp row = 32 consecutive int16 of one channel ---- */
+            /* ---- phase 3: coalesced copy-out; warp e owns channels 4e..4e+3, lanes run along time ---- */
             {
                 const int kofs = t * TC_KP - 1;
                 int ncol = K32 - kofs;                                  /* valid columns are 1 .. ncol-1 */
                 if (ncol > TC_N) ncol = TC_N;
-                for (int idx = et; idx < TC_CH * TC_N; idx += EPI_THREADS) {
-                    const int chn = idx >> 6, colx = idx & 63;
+                const bool ok0 = lane >= 1 && lane < ncol, ok1 = lane + 32 < ncol;
+#pragma unroll
+                for (int j = 0; j < TC_CH / EPI_WARPS; j++) {
+                    const int chn = e * (TC_CH / EPI_WARPS) + j;
                     const int cg = g * TC_CH + chn;
-                    if (colx >= 1 && colx < ncol && cg < p.C)
-                        p.pcm[(size_t)cg * p.pitch + kofs + colx] = pcmbuf[colx * PCM_PITCH + chn];
+                    if (cg < p.C) {
+                        short *dst = p.pcm + (size_t)cg * p.pitch + kofs;
+                        if (ok0) dst[lane] = pcmbuf[lane * PCM_PITCH + chn];
+                        if (ok1) dst[lane + 32] = pcmbuf[(lane + 32) * PCM_PITCH + chn];
+                    }
                 }
             }
         }

@@ -97,6 +97,9 @@ class GpuChan:
     def submit_device(self, dev_ptr: int, n_complex: int, stream: int = 0):
         _check(self._L.gpuchan_submit_device(self._h, dev_ptr, n_complex, stream), "gpuchan_submit_device")
 
+    def stream_wait(self, stream: int):
+        _check(self._L.gpuchan_stream_wait(self._h, stream), "gpuchan_stream_wait")
+
     def sync(self):
         _check(self._L.gpuchan_sync(self._h), "gpuchan_sync")
 
