@@ -580,13 +580,9 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
         tc_build_tap_image(h->tc, h->h_re.data(), h->h_im.data(), img);
         FAIL_TRY(cudaMalloc(&h->d_tap_img, img.size()));
         FAIL_TRY(cudaMemcpy(h->d_tap_img, img.data(), img.size(), cudaMemcpyHostToDevice));
-        h->plane_rows = (long long)h->ckpt_tiles * TC_KP + h->tc.Q + 72;
-        const size_t plane_bytes = (size_t)h->tc.Kp * h->plane_rows;
         FAIL_TRY(cudaStreamCreateWithFlags(&h->s_pre, cudaStreamNonBlocking));
         FAIL_TRY(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) {
-            FAIL_TRY(cudaMalloc(&h->d_plane_hi[i], plane_bytes));
-            FAIL_TRY(cudaMalloc(&h->d_plane_lo[i], plane_bytes));
             FAIL_TRY(cudaEventCreateWithFlags(&h->ev_pre_done[i], cudaEventDisableTiming));
             FAIL_TRY(cudaEventCreateWithFlags(&h->ev_main_done[i], cudaEventDisableTiming));
         }
@@ -737,14 +733,7 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
     }
 
     TcBatch tb;
-    if (use_tc && K > 0) {
-        tb.in = in;
-        tb.plane_hi = h->d_plane_hi[pb]; tb.plane_lo = h->d_plane_lo[pb];
-        tb.Mrows = (long long)nr_tiles * TC_KP + h->tc.Q + 8;
-        if (tb.Mrows > h->plane_rows) return set_err(GPUCHAN_E_INVAL, "internal plane capacity exceeded");
-        CUDA_TRY(tc_launch_deinterleave(h->tc, tb, pre));
-        h->launches++;
-    }
+    tb.in = in;
 
     /* keep what the next submit still needs: samples [K*D, avail).  (IMAD engine: after the FIR kernel, see below) */
     const long long from = (long long)K * D;

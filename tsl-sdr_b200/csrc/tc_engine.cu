@@ -13,13 +13,14 @@
  * (weights 2^16, 2^8, 1) that are recombined modulo 2^32 in the epilogue -- bit-identical to the reference's
  * wrapping int32 sum.  When every tap entry fits in int8 (typical narrow low-pass at unit gain) one limb suffices.
  *
- * Kernels:
- *   tc_deinterleave_kernel  raw cs16 stream -> two byte planes (hi s8 / lo u8) in "slab" order
- *                           [16-byte K slab][block-row][16 B], zero padded to Kp = round_up(2D, 32) bytes per row
- *   tc_fir_fm_kernel        persistent, warp specialised: warp 0 streams sample tiles with cp.async.bulk (UBLKCP)
- *                           into a 2-stage smem ring, warp 1 issues tcgen05.mma kind::i8 (UTCIMMA) into a 2-stage
- *                           TMEM ring, warps 2-9 drain TMEM (LDTM) and run the exact epilogue: limb recombination,
- *                           rq, derotator recurrence, discriminator (fm_math.cuh), int16 PCM stores.
+ * Kernel:
+ *   tc_fir_fm_kernel        persistent, warp specialised (21 warps):
+ *     warps 0-3   transform: read the raw cs16 tile once from HBM/L2 and split it into two byte planes (hi s8 / lo u8)
+ *                 in "slab" order [16-byte K slab][block-row][16 B] (rows zero padded to Kp = round_up(2D, 32) bytes)
+ *                 directly in a 2-stage shared-memory ring;
+ *     warp  4     issues tcgen05.mma kind::i8 (SASS UTCIMMA) from precomputed descriptors into a 2-stage TMEM ring;
+ *     warps 5-20  drain TMEM (LDTM), recombine the limbs, and run the exact epilogue: rq, derotator recurrence,
+ *                 discriminator (fm_math.cuh), int16 PCM, coalesced stores through shared memory.
  * The B operand needs no im2col: with K-major / no-swizzle descriptors the Q row shifts are just +16 B on the
  * operand start address (validated by tc_selftest.cu).
  */
@@ -34,37 +35,19 @@ namespace tslb200 {
 namespace {
 
 constexpr int EPI_WARPS = 16;
-constexpr int TC_THREADS = 32 * (2 + EPI_WARPS);    /* producer warp, MMA warp, epilogue warps */
+constexpr int XF_WARPS = 4;             /* transform warps: raw cs16 -> byte planes in smem */
+constexpr int XF_THREADS = 32 * XF_WARPS;
+constexpr int MMA_WARP = XF_WARPS;      /* warp index of the MMA issuer */
+constexpr int EPI_WARP0 = XF_WARPS + 1; /* first epilogue warp (EPI_WARP0 % 4 == 1: any 4 consecutive warps cover all TMEM slices) */
+constexpr int TC_THREADS = 32 * (XF_WARPS + 1 + EPI_WARPS);
+constexpr int MAX_KSTEPS = 64;          /* Q * (Kp/32) descriptors kept in shared memory */
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int PCM_PITCH = 66;           /* int16 per column row: 64 channels + 2 pad -> 33 words, conflict-free both ways */
 
 /* ---------------------------------------------------------------------------------------------- */
-__global__ void tc_deinterleave_kernel(InWindow in, int D, int nslab, long long Mrows, uint8_t *__restrict__ plane_hi,
-                                       uint8_t *__restrict__ plane_lo)
-{
-    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;   /* block-row: samples [(m-1)D, mD) */
-    const int j = blockIdx.y;                                               /* 16-byte slab = int16 elements 16j.. = samples 8j.. */
-    if (m >= Mrows) return;
-    const long long s0 = (m - 1) * (long long)D + 8 * j;
-    uint32_t w[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) w[u] = (8 * j + u < D) ? (uint32_t)in_sample(in, s0 + u) : 0u;
-    uint4 lo, hi;
-    /* packed sample = bytes (lo(re), hi(re), lo(im), hi(im)) */
-    lo.x = __byte_perm(w[0], w[1], 0x6420); hi.x = __byte_perm(w[0], w[1], 0x7531);
-    lo.y = __byte_perm(w[2], w[3], 0x6420); hi.y = __byte_perm(w[2], w[3], 0x7531);
-    lo.z = __byte_perm(w[4], w[5], 0x6420); hi.z = __byte_perm(w[4], w[5], 0x7531);
-    lo.w = __byte_perm(w[6], w[7], 0x6420); hi.w = __byte_perm(w[6], w[7], 0x7531);
-    const size_t off = ((size_t)j * Mrows + m) * 16;
-    *reinterpret_cast<uint4 *>(plane_lo + off) = lo;
-    *reinterpret_cast<uint4 *>(plane_hi + off) = hi;
-    (void)nslab;
-}
-
-/* ---------------------------------------------------------------------------------------------- */
 struct TcKernelParams {
-    const uint8_t *plane_hi, *plane_lo;
-    long long Mrows;
+    InWindow in;            /* raw interleaved int16 I,Q stream of this submit: [carry | fresh] */
+    int D;
     const uint8_t *tap_img;
     const int *incr, *ckpt, *last_in;
     int *last_out;
@@ -86,6 +69,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
     __shared__ __align__(8) uint64_t b_full[2], b_empty[2], t_full[2], t_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float2 atan_s[256];
+    __shared__ __align__(8) uint64_t descA[MAX_KSTEPS * 2];       /* [q*nchunk + kk][limb] */
+    __shared__ __align__(8) uint64_t descB[2 * 2 * MAX_KSTEPS];   /* [stage][plane][q*nchunk + kk] */
 
     uint8_t *sA = smem;                                         /* [Q][LIMBS][nslab][128][16] */
     uint8_t *sB = smem + p.a_group_bytes;                       /* [2 stages][2 planes][nslab][R][16] */
@@ -105,12 +90,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
     }
     if (tid == 0) {
         for (int s = 0; s < 2; s++) {
-            ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1);
+            ptx::mbar_init(&b_full[s], XF_WARPS); ptx::mbar_init(&b_empty[s], 1);
             ptx::mbar_init(&t_full[s], 1); ptx::mbar_init(&t_empty[s], EPI_WARPS);
         }
         ptx::fence_mbar_init();
     }
-    if (warp == 1) ptx::tmem_alloc(&tmem_base_s, 512);
+    if (warp == MMA_WARP) ptx::tmem_alloc(&tmem_base_s, 512);
+    {   /* operand descriptors are tile-invariant: build them once */
+        const uint32_t a_mat_bytes = (uint32_t)p.Kp * 128, slab_bytes = (uint32_t)p.R * 16;
+        const int nsteps = p.Q * nchunk;
+        for (int i = tid; i < nsteps * 2; i += TC_THREADS) {
+            const int step = i >> 1, limb = i & 1, q = step / nchunk, kk = step - q * nchunk;
+            if (limb < LIMBS)
+                descA[i] = ptx::smem_desc_kmajor_noswz(ptx::smem_u32(sA) + (uint32_t)(q * LIMBS + limb) * a_mat_bytes + kk * 2 * 2048, 2048, 128);
+        }
+        for (int i = tid; i < nsteps * 4; i += TC_THREADS) {
+            const int step = i % nsteps, pl = (i / nsteps) & 1, st = i / (2 * nsteps);
+            const int q = step / nchunk, kk = step - q * nchunk;
+            const uint32_t base = ptx::smem_u32(sB) + (uint32_t)st * p.b_stage_bytes + (uint32_t)pl * nslab * slab_bytes;
+            descB[(st * 2 + pl) * MAX_KSTEPS + step] = ptx::smem_desc_kmajor_noswz(base + kk * 2 * slab_bytes + q * 16, slab_bytes, 128);
+        }
+    }
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
     __syncthreads();
@@ -118,35 +118,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
     const uint32_t tmem_base = tmem_base_s;
 #define DBG(role, it, slot) do { if (p.dbg && blockIdx.x == 0 && (it) < 32) p.dbg[((role) * 32 + (it)) * 8 + (slot)] = clock64(); } while (0)
 
-    if (warp == 0) {
-        /* ================= producer: sample tiles -> smem ring ================= */
-        if (lane == 0) {
-            int it = 0;
-            for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
-                const int s = it & 1, ph = (it >> 1) & 1;
-                DBG(0, it, 0);
-                ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1);
-                DBG(0, it, 1);
-                ptx::mbar_arrive_expect_tx(&b_full[s], p.b_stage_bytes);
-                uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
-                const uint32_t slab_bytes = (uint32_t)p.R * 16;
-                const size_t row0 = (size_t)t * TC_KP;
-                for (int j = 0; j < nslab; j++) {
-                    ptx::bulk_g2s(dst + (size_t)j * slab_bytes, p.plane_hi + ((size_t)j * p.Mrows + row0) * 16, slab_bytes, &b_full[s]);
-                    ptx::bulk_g2s(dst + (size_t)(nslab + j) * slab_bytes, p.plane_lo + ((size_t)j * p.Mrows + row0) * 16, slab_bytes, &b_full[s]);
-                }
-                DBG(0, it, 2);
+    if (warp < XF_WARPS) {
+        /* ================= transform: raw cs16 samples -> hi/lo byte planes of the smem ring =================
+         * Plane row m of tile t = stream samples [(t*63 + m - 1) * D, +D); item (m, j) is one 16-byte slab entry
+         * = 8 complex samples = 32 raw bytes.  Consecutive threads take consecutive j: 32-byte pieces of one
+         * contiguous run, so the global reads coalesce. */
+        const int items = p.R * nslab;
+        const uint32_t slab_bytes = (uint32_t)p.R * 16;
+        int it = 0;
+        for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
+            const int s = it & 1, ph = (it >> 1) & 1;
+            if (tid == 0) DBG(0, it, 0);
+            ptx::mbar_wait(&b_empty[s], ph ^ 1);
+            if (tid == 0) DBG(0, it, 1);
+            uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
+            const long long row_base = (long long)t * TC_KP - 1;
+            for (int item = tid; item < items; item += XF_THREADS) {
+                const int m = item / nslab, j = item - m * nslab;
+                const long long s0 = (row_base + m) * (long long)p.D + 8 * j;
+                uint32_t w[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) w[u] = (8 * j + u < p.D) ? (uint32_t)in_sample(p.in, s0 + u) : 0u;
+                uint4 lo, hi;       /* packed sample = bytes (lo(re), hi(re), lo(im), hi(im)) */
+                lo.x = __byte_perm(w[0], w[1], 0x6420); hi.x = __byte_perm(w[0], w[1], 0x7531);
+                lo.y = __byte_perm(w[2], w[3], 0x6420); hi.y = __byte_perm(w[2], w[3], 0x7531);
+                lo.z = __byte_perm(w[4], w[5], 0x6420); hi.z = __byte_perm(w[4], w[5], 0x7531);
+                lo.w = __byte_perm(w[6], w[7], 0x6420); hi.w = __byte_perm(w[6], w[7], 0x7531);
+                *reinterpret_cast<uint4 *>(dst + (size_t)j * slab_bytes + m * 16) = hi;
+                *reinterpret_cast<uint4 *>(dst + (size_t)(nslab + j) * slab_bytes + m * 16) = lo;
             }
+            ptx::fence_proxy_async();       /* generic-proxy stores -> visible to the tensor core's async proxy */
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&b_full[s]);
+            if (tid == 0) DBG(0, it, 2);
         }
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         /* ================= MMA issuer ================= */
         if (lane == 0) {
             const uint32_t id_ss = ptx::idesc_i8(128, TC_N, true, true);    /* A s8, B s8 */
             const uint32_t id_su = ptx::idesc_i8(128, TC_N, true, false);   /* A s8, B u8 */
             const uint32_t id_us = ptx::idesc_i8(128, TC_N, false, true);
             const uint32_t id_uu = ptx::idesc_i8(128, TC_N, false, false);
-            const uint32_t a_mat_bytes = (uint32_t)p.Kp * 128;              /* one (q, limb) tap matrix */
-            const uint32_t slab_bytes = (uint32_t)p.R * 16;
             int it = 0;
             for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
                 const int s = it & 1, ph = (it >> 1) & 1;
@@ -157,26 +169,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
                 DBG(1, it, 2);
                 ptx::tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)s * 256;         /* slots: +0 (2^16), +64 (2^8), +128 (1) */
-                const uint32_t b_hi = ptx::smem_u32(sB + (size_t)s * p.b_stage_bytes);
-                const uint32_t b_lo = b_hi + (uint32_t)nslab * slab_bytes;
-                uint32_t first_hh = 0, first_mid = 0, first_ll = 0;
-                for (int q = 0; q < p.Q; q++) {
-                    const uint32_t a_q = ptx::smem_u32(sA) + (uint32_t)(q * LIMBS) * a_mat_bytes;
-                    for (int kk = 0; kk < nchunk; kk++) {
-                        const uint64_t dbh = ptx::smem_desc_kmajor_noswz(b_hi + kk * 2 * slab_bytes + q * 16, slab_bytes, 128);
-                        const uint64_t dbl = ptx::smem_desc_kmajor_noswz(b_lo + kk * 2 * slab_bytes + q * 16, slab_bytes, 128);
-                        if (LIMBS == 2) {
-                            const uint64_t dah = ptx::smem_desc_kmajor_noswz(a_q + a_mat_bytes + kk * 2 * 2048, 2048, 128);
-                            const uint64_t dal = ptx::smem_desc_kmajor_noswz(a_q + kk * 2 * 2048, 2048, 128);
-                            ptx::mma_i8(acc + 0,   dah, dbh, id_ss, first_hh);  first_hh = 1;
-                            ptx::mma_i8(acc + 64,  dah, dbl, id_su, first_mid); first_mid = 1;
-                            ptx::mma_i8(acc + 64,  dal, dbh, id_us, 1);
-                            ptx::mma_i8(acc + 128, dal, dbl, id_uu, first_ll);  first_ll = 1;
-                        } else {
-                            const uint64_t da = ptx::smem_desc_kmajor_noswz(a_q + kk * 2 * 2048, 2048, 128);
-                            ptx::mma_i8(acc + 64,  da, dbh, id_ss, first_mid); first_mid = 1;
-                            ptx::mma_i8(acc + 128, da, dbl, id_su, first_ll);  first_ll = 1;
-                        }
+                const uint64_t *dbh_p = descB + (s * 2 + 0) * MAX_KSTEPS, *dbl_p = descB + (s * 2 + 1) * MAX_KSTEPS;
+                const int nsteps = p.Q * nchunk;
+                for (int st = 0; st < nsteps; st++) {
+                    const uint64_t dbh = dbh_p[st], dbl = dbl_p[st];
+                    const uint32_t accum = st > 0;
+                    if (LIMBS == 2) {
+                        const uint64_t dal = descA[2 * st], dah = descA[2 * st + 1];
+                        ptx::mma_i8(acc + 0,   dah, dbh, id_ss, accum);
+                        ptx::mma_i8(acc + 64,  dah, dbl, id_su, accum);
+                        ptx::mma_i8(acc + 64,  dal, dbh, id_us, 1);
+                        ptx::mma_i8(acc + 128, dal, dbl, id_uu, accum);
+                    } else {
+                        const uint64_t da = descA[2 * st];
+                        ptx::mma_i8(acc + 64,  da, dbh, id_ss, accum);
+                        ptx::mma_i8(acc + 128, da, dbl, id_su, accum);
                     }
                 }
                 DBG(1, it, 3);
@@ -187,13 +194,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
         }
     } else {
         /* ================= epilogue: TMEM -> smem -> derotate -> discriminate -> PCM ================= */
-        const int e = warp - 2;
+        const int e = warp - EPI_WARP0;
         const int slice = warp & 3;                 /* TMEM lanes 32*slice .. +31 are the only ones this warp may read */
         const int quarter = e >> 2;                 /* which 16-column quarter of the tile this warp drains */
         const int row = 32 * slice + lane;          /* accumulator row: 2*channel + (0 = re, 1 = im) */
         const uint32_t lane_base = (uint32_t)(32 * slice) << 16;
         /* compute mapping: consecutive lanes = consecutive channels (conflict-free smem reads) */
-        const int et = tid - 64;                    /* 0 .. EPI_THREADS-1 */
+        const int et = tid - 32 * EPI_WARP0;        /* 0 .. EPI_THREADS-1 */
         const int ch = et & 63;
         const int r = et >> 6;                      /* TC_STEP-column range this thread turns into PCM */
         const int c0 = TC_STEP * r;
@@ -208,9 +215,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
         int it = 0;
         for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
             const int s = it & 1, ph = (it >> 1) & 1;
-            if (tid == 64) DBG(2, it, 0);
+            if (et == 0) DBG(2, it, 0);
             ptx::mbar_wait(&t_full[s], ph);
-            if (tid == 64) DBG(2, it, 1);
+            if (et == 0) DBG(2, it, 1);
             ptx::tc_fence_after();
             /* ---- phase 1: drain TMEM, recombine the limbs modulo 2^32, park in smem as [column][row] ---- */
             {
@@ -228,9 +235,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&t_empty[s]);   /* TMEM stage is free again */
-            if (tid == 64) DBG(2, it, 2);
+            if (et == 0) DBG(2, it, 2);
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      /* all 64 columns parked */
-            if (tid == 64) DBG(2, it, 3);
+            if (et == 0) DBG(2, it, 3);
 
             /* ---- phase 2: one channel x TC_STEP columns per thread ---- */
             if (live) {
@@ -270,9 +277,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
                 /* the thread that produced the submit's last output hands y[K-1] to the next submit */
                 if (produced && kofs + col_end == K32) p.last_out[c] = pack16(p_re, p_im);
             }
-            if (tid == 64) DBG(2, it, 4);
+            if (et == 0) DBG(2, it, 4);
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      /* accbuf free; the tile's PCM is complete in smem */
-            if (tid == 64) DBG(2, it, 5);
+            if (et == 0) DBG(2, it, 5);
             /* ---- phase 3: coalesced copy-out; warp e owns channels 4e..4e+3, lanes run along time ---- */
             {
                 const int kofs = t * TC_KP - 1;
@@ -295,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+    if (warp == MMA_WARP) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 } // namespace
@@ -334,9 +341,10 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
     pl.a_group_bytes = (size_t)pl.Q * pl.limbs * pl.Kp * 128;
     pl.b_stage_bytes = (size_t)2 * pl.Kp * pl.R;
     pl.smem_bytes = pl.a_group_bytes + 2 * pl.b_stage_bytes + (size_t)TC_N * 128 * 4 + (size_t)TC_N * 66 * 2 + 128;
-    const size_t static_smem = 2048 + 256;
+    const size_t static_smem = 5248 + 256;  /* atan table, descriptors, barriers */
     if (pl.smem_bytes + static_smem > (size_t)smem_max) { pl.why = "tap image + sample ring exceed shared memory"; return pl; }
     if ((size_t)pl.R * 16 >= (1u << 18)) { pl.why = "tile too tall for the descriptor"; return pl; }
+    if (pl.Q * (pl.Kp / 32) > 64) { pl.why = "too many K steps (taps / decimation too large)"; return pl; }
     pl.ok = true;
     return pl;
 }
@@ -365,17 +373,10 @@ void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_
                 }
 }
 
-cudaError_t tc_launch_deinterleave(const TcPlan &pl, const TcBatch &b, cudaStream_t st)
-{
-    dim3 grid((unsigned)((b.Mrows + 127) / 128), pl.Kp / 16);
-    tc_deinterleave_kernel<<<grid, 128, 0, st>>>(b.in, pl.D, pl.Kp / 16, b.Mrows, b.plane_hi, b.plane_lo);
-    return cudaGetLastError();
-}
-
 cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, int nr_sms, cudaStream_t st)
 {
     TcKernelParams p;
-    p.plane_hi = b.plane_hi; p.plane_lo = b.plane_lo; p.Mrows = b.Mrows;
+    p.in = b.in; p.D = pl.D;
     p.tap_img = b.tap_img; p.incr = b.incr; p.ckpt = b.ckpt; p.last_in = b.last_in; p.last_out = b.last_out;
     p.atan_tab = b.atan_tab; p.pcm = b.pcm; p.iq_out = b.iq_out; p.pitch = b.pitch; p.K = b.K;
     p.nr_tiles = b.nr_tiles; p.C = pl.C; p.G = pl.G; p.Kp = pl.Kp; p.Q = pl.Q; p.R = pl.R;

@@ -34,8 +34,6 @@ void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_
 
 struct TcBatch {
     InWindow in;
-    uint8_t *plane_hi, *plane_lo;       /* [Kp/16][Mrows][16] */
-    long long Mrows;
     const uint8_t *tap_img;
     const int *incr, *ckpt, *last_in;
     int *last_out;
@@ -49,7 +47,6 @@ struct TcBatch {
     long long *dbg = nullptr;
 };
 
-cudaError_t tc_launch_deinterleave(const TcPlan &pl, const TcBatch &b, cudaStream_t st);
 cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, int nr_sms, cudaStream_t st);
 
 } // namespace tslb200
