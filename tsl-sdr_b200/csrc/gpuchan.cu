@@ -144,22 +144,40 @@ __global__ void rot_cycle_detect_kernel(const int *__restrict__ incr, int nr_cha
 }
 
 /* -------------------------------------------------------------------------------------- */
-/* Per submit: derotator phase checkpoints.  Tile t covers FIR outputs (columns) j = 0..KT-1 <-> stream output
- * index k0 + t*KP - 1 + j (KP = KT-1); column 0 only feeds the discriminator's "previous sample".
- * There are `sub` checkpoints per tile: r = 0 is the phase of column 0 (column 1 for the first tile of a
- * submit, whose column 0 is the previous submit's last output), r > 0 the phase of column step*r-1.
- * ckpt[(t*sub + r)*C + c]. */
-__device__ __forceinline__ unsigned long long ckpt_index(unsigned long long k0, int t, int r, int KP, int step)
+/* Per submit: derotator phase checkpoints, ckpt[(t*sub + r)*C + c], one for every (tile t, sub-block r) an engine
+ * starts a run of consecutive outputs at.  ckpt_local() gives the output index (relative to the submit) whose
+ * phase is stored, or -1 for an entry nobody reads.  Entries are visited in increasing output order.
+ *
+ * IMAD engine (mode 0): tile t covers FIR outputs (columns) j = 0..KT-1 <-> output t*KP - 1 + j (KP = KT-1); column
+ *   0 only feeds the discriminator's "previous sample".  r = 0 is the phase of column 0 (column 1 for the first tile
+ *   of a submit, whose column 0 is the previous submit's last output), r > 0 the phase of column step*r-1.
+ * Tensor-core engine (mode 1): tile t = chunk j * n + i covers outputs j*L - 8 + 64*i + [0, 64) (tc_engine.cuh).
+ *   r > 0: phase of column 8r-1, the previous sample of sub-block r (clamped to output 0 for the very first output
+ *   of the submit, whose previous sample is carried state); r = 0: phase of column 0 (its previous sample crosses
+ *   tiles through shared memory); unused for the first tile of a chunk, whose first 8 columns are lead-in. */
+struct CkptGeom {
+    int mode;
+    int KP, sub, step;      /* mode 0 */
+    int n;                  /* mode 1: tiles per chunk */
+    long long L;            /* mode 1: outputs per chunk */
+};
+
+__device__ __forceinline__ long long ckpt_local(const CkptGeom &gm, int t, int r)
 {
-    const long long col = (r == 0) ? 0 : step * r - 1;
-    const long long g = (long long)k0 + (long long)t * KP + col - 1 + ((t == 0 && r == 0) ? 1 : 0);
-    return (unsigned long long)g;
+    if (gm.mode == 0) {
+        const long long col = (r == 0) ? 0 : gm.step * r - 1;
+        return (long long)t * gm.KP + col - 1 + ((t == 0 && r == 0) ? 1 : 0);
+    }
+    const int j = t / gm.n, i = t - j * gm.n;
+    if (r == 0 && i == 0) return -1;
+    const long long v = (long long)j * gm.L - 8 + 64LL * i + (r == 0 ? 0 : 8 * r - 1);
+    return v < 0 ? 0 : v;
 }
 
 __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict__ rot_state, int nr_channels,
                                    const uint32_t *__restrict__ mu, const uint32_t *__restrict__ lambda,
                                    const int *__restrict__ cyc, unsigned long long k0, unsigned long long K,
-                                   int KP, int sub, int step, int nr_tiles, int *__restrict__ ckpt)
+                                   CkptGeom gm, int nr_tiles, int *__restrict__ ckpt)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nr_channels) return;
@@ -180,12 +198,12 @@ __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict
     };
 
     for (int t = 0; t < nr_tiles; t++)
-        for (int r = 0; r < sub; r++) {
-            const unsigned long long g = ckpt_index(k0, t, r, KP, step);
-            if (g > k0 + K) continue;           /* past the last output of this submit: never read, and the
-                                                   sequential walk must not overshoot the state we hand on */
-            seek(g);
-            ckpt[((size_t)t * sub + r) * nr_channels + c] = pack16(r_re, r_im);
+        for (int r = 0; r < gm.sub; r++) {
+            const long long loc = ckpt_local(gm, t, r);
+            if (loc < 0 || (unsigned long long)loc > K) continue;   /* unused, or past the last output of this submit: never
+                                                   read, and the sequential walk must not overshoot the state we hand on */
+            seek(k0 + (unsigned long long)loc);
+            ckpt[((size_t)t * gm.sub + r) * nr_channels + c] = pack16(r_re, r_im);
         }
     seek(k0 + K);
     rot_state[c] = pack16(r_re, r_im);
@@ -195,7 +213,7 @@ __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict
  * every checkpoint is an independent table lookup. */
 __global__ void rot_prepass_table_kernel(int *__restrict__ rot_state, int nr_channels, const uint32_t *__restrict__ mu,
                                          const uint32_t *__restrict__ lambda, const int *__restrict__ cyc,
-                                         unsigned long long k0, unsigned long long K, int KP, int sub, int step,
+                                         unsigned long long k0, unsigned long long K, CkptGeom gm,
                                          int nr_tiles, int *__restrict__ ckpt)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,14 +223,18 @@ __global__ void rot_prepass_table_kernel(int *__restrict__ rot_state, int nr_cha
     const int t_begin = blockIdx.y * 16;
     const int t_end = min(nr_tiles, t_begin + 16);
     if (t_begin >= nr_tiles) return;
-    unsigned long long prev = ckpt_index(k0, t_begin, 0, KP, step);
-    uint32_t ph = (uint32_t)((prev - m) % lam);             /* one 64-bit division per thread */
+    bool have = false;
+    unsigned long long prev = 0;
+    uint32_t ph = 0;
     for (int t = t_begin; t < t_end; t++)
-        for (int r = 0; r < sub; r++) {
-            const unsigned long long g = ckpt_index(k0, t, r, KP, step);
-            ph = (ph + (uint32_t)(g - prev)) % lam;
+        for (int r = 0; r < gm.sub; r++) {
+            const long long loc = ckpt_local(gm, t, r);
+            if (loc < 0) continue;
+            const unsigned long long g = k0 + (unsigned long long)loc;
+            if (!have) { ph = (uint32_t)((g - m) % lam); have = true; }       /* one 64-bit division per thread */
+            else ph = (ph + (uint32_t)(g - prev)) % lam;
             prev = g;
-            ckpt[((size_t)t * sub + r) * nr_channels + c] = tab[ph];
+            ckpt[((size_t)t * gm.sub + r) * nr_channels + c] = tab[ph];
         }
     if (blockIdx.y == 0) rot_state[c] = tab[(k0 + K - m) % lam];
 }
@@ -568,12 +590,12 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
     }
 
     const bool use_tc = h->engine == GPUCHAN_ENGINE_TC;
-    const int KP = use_tc ? TC_KP : FIR_WARPS * h->R - 1;
+    const int KP = FIR_WARPS * h->R - 1;
     const int sub = use_tc ? TC_SUB : 1;
     const size_t max_avail = h->max_batch + (size_t)T;
     const size_t max_K = max_avail / h->D + 2;
     h->pitch = (max_K + 63) & ~(size_t)63;
-    h->ckpt_tiles = (max_K + KP - 1) / KP + 1;
+    h->ckpt_tiles = use_tc ? tc_max_ckpt_tiles(h->tc, (long long)max_K, h->nr_sms) : (max_K + KP - 1) / KP + 1;
 
     if (use_tc) {
         std::vector<uint8_t> img;
@@ -715,18 +737,26 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
     }
     int *ckpt = (use_tc && pb) ? h->d_ckpt2 : h->d_ckpt;
 
-    const int KP = use_tc ? TC_KP : FIR_WARPS * h->R - 1;
-    const int sub = use_tc ? TC_SUB : 1;
-    const int nr_tiles = (int)((K + KP - 1) / KP);
+    CkptGeom cg{};
+    TcGeom tg;
+    int nr_tiles;
+    if (use_tc) {
+        tg = tc_geometry(h->tc, (long long)K, h->nr_sms);
+        cg.mode = 1; cg.sub = TC_SUB; cg.n = tg.n_tiles > 0 ? tg.n_tiles : 1; cg.L = tg.L;
+        nr_tiles = tg.chunks * tg.n_tiles;
+    } else {
+        cg.mode = 0; cg.KP = FIR_WARPS * h->R - 1; cg.sub = 1; cg.step = 16;
+        nr_tiles = (int)((K + cg.KP - 1) / cg.KP);
+    }
     if (K > 0) {
         if ((size_t)nr_tiles > h->ckpt_tiles || K > h->pitch) return set_err(GPUCHAN_E_INVAL, "internal capacity exceeded");
         if (h->all_cyclic && h->k_total >= h->mu_max + 1) {
             dim3 g((h->C + 63) / 64, (nr_tiles + 15) / 16);
-            rot_prepass_table_kernel<<<g, 64, 0, pre>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, KP, sub,
-                                                        use_tc ? TC_STEP : 16, nr_tiles, ckpt);
+            rot_prepass_table_kernel<<<g, 64, 0, pre>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, cg,
+                                                        nr_tiles, ckpt);
         } else {
             rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, pre>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
-                                                                 h->k_total, K, KP, sub, use_tc ? TC_STEP : 16, nr_tiles, ckpt);
+                                                                 h->k_total, K, cg, nr_tiles, ckpt);
         }
         h->launches++;
         CUDA_TRY(cudaGetLastError());
@@ -764,9 +794,9 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
             tb.tap_img = h->d_tap_img; tb.incr = h->d_incr; tb.ckpt = ckpt;
             tb.last_in = h->d_last[h->pp_last]; tb.last_out = h->d_last[h->pp_last ^ 1];
             tb.atan_tab = h->d_atan; tb.pcm = h->d_pcm[slot]; tb.iq_out = h->d_iq[slot]; tb.pitch = (long long)h->pitch;
-            tb.K = K; tb.nr_tiles = nr_tiles; tb.atan = h->atan;
+            tb.K = K; tb.geom = tg; tb.atan = h->atan;
             tb.dbg = h->d_dbg;
-            CUDA_TRY(tc_launch_fir_fm(h->tc, tb, h->nr_sms, st));
+            CUDA_TRY(tc_launch_fir_fm(h->tc, tb, st));
             h->launches++;
         } else {
             FirFmParams p;

@@ -42,7 +42,6 @@ constexpr int EPI_WARP0 = XF_WARPS + 1; /* first epilogue warp (EPI_WARP0 % 4 ==
 constexpr int TC_THREADS = 32 * (XF_WARPS + 1 + EPI_WARPS);
 constexpr int MAX_KSTEPS = 64;          /* Q * (Kp/32) descriptors kept in shared memory */
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
-constexpr int PCM_PITCH = 66;           /* int16 per column row: 64 channels + 2 pad -> 33 words, conflict-free both ways */
 
 /* ---------------------------------------------------------------------------------------------- */
 struct TcKernelParams {
@@ -55,31 +54,77 @@ struct TcKernelParams {
     short *pcm;
     int *iq_out;
     long long pitch;
-    unsigned long long K;
-    int nr_tiles, C, G, Kp, Q, R;
+    long long K;            /* outputs per channel of this submit */
+    long long L;            /* outputs per chunk (64 * n_tiles - 8) */
+    int n_tiles;            /* tiles per chunk */
+    int C, G, Kp, Q, R;
+    float inv_nslab;
     uint32_t a_group_bytes, b_stage_bytes;
     AtanParams atan;
     long long *dbg;         /* optional per-role clock stamps of CTA 0 (bench diagnostics) */
 };
 
-template <int LIMBS>
+/* 8 consecutive raw samples starting at a (4-byte aligned, inside the fresh buffer with >= 12 samples of slack):
+ * three aligned 16-byte loads, then a word rotation by o = (address / 4) mod 4. */
+__device__ __forceinline__ void load8_unaligned(const int *a, uint32_t (&w)[8])
+{
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(a);
+    const uint4 *al = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
+    const uint32_t o = (uint32_t)(addr >> 2) & 3u;
+    const uint4 v0 = __ldg(al), v1 = __ldg(al + 1);
+    uint4 v2 = make_uint4(0, 0, 0, 0);
+    if (o) v2 = __ldg(al + 2);
+    const bool o2 = (o & 2u) != 0, o1 = (o & 1u) != 0;
+    /* stage 1: drop 2 words if o2 */
+    const uint32_t t0 = o2 ? v0.z : v0.x, t1 = o2 ? v0.w : v0.y, t2 = o2 ? v1.x : v0.z, t3 = o2 ? v1.y : v0.w,
+                   t4 = o2 ? v1.z : v1.x, t5 = o2 ? v1.w : v1.y, t6 = o2 ? v2.x : v1.z, t7 = o2 ? v2.y : v1.w,
+                   t8 = o2 ? v2.z : v2.x;
+    /* stage 2: drop 1 word if o1 */
+    w[0] = o1 ? t1 : t0; w[1] = o1 ? t2 : t1; w[2] = o1 ? t3 : t2; w[3] = o1 ? t4 : t3;
+    w[4] = o1 ? t5 : t4; w[5] = o1 ? t6 : t5; w[6] = o1 ? t7 : t6; w[7] = o1 ? t8 : t7;
+}
+
+/* packed sample = bytes (lo(re), hi(re), lo(im), hi(im)): split 8 samples into a hi and a lo 16-byte slab entry */
+__device__ __forceinline__ void split_store(const uint32_t (&w)[8], uint8_t *hi_dst, uint8_t *lo_dst)
+{
+    uint4 lo, hi;
+    lo.x = __byte_perm(w[0], w[1], 0x6420); hi.x = __byte_perm(w[0], w[1], 0x7531);
+    lo.y = __byte_perm(w[2], w[3], 0x6420); hi.y = __byte_perm(w[2], w[3], 0x7531);
+    lo.z = __byte_perm(w[4], w[5], 0x6420); hi.z = __byte_perm(w[4], w[5], 0x7531);
+    lo.w = __byte_perm(w[6], w[7], 0x6420); hi.w = __byte_perm(w[6], w[7], 0x7531);
+    *reinterpret_cast<uint4 *>(hi_dst) = hi;
+    *reinterpret_cast<uint4 *>(lo_dst) = lo;
+}
+
+/*
+ * Work decomposition.  The K outputs of a submit are cut into `chunks` contiguous ranges of L = 64*n - 8 outputs,
+ * one per CTA of a channel group; a CTA walks its range in n tiles of 64 FIR outputs (columns).  Tile i of chunk j
+ * covers outputs j*L - 8 + 64*i + [0, 64): the first 8 columns of a chunk belong to the previous chunk and are only
+ * computed so that column 7 can serve as the discriminator's "previous sample" of the chunk's first output.  Inside a
+ * chunk the previous sample crosses tiles through shared memory.  Every epilogue thread therefore owns 8 consecutive
+ * outputs whose index is a multiple of 8: one 16-byte PCM store.
+ */
+template <int LIMBS, bool KEEP_IQ, bool FMA>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernelParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t b_full[2], b_empty[2], t_full[2], t_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float2 atan_s[256];
+    __shared__ int yprev_s[2][TC_CH];
     __shared__ __align__(8) uint64_t descA[MAX_KSTEPS * 2];       /* [q*nchunk + kk][limb] */
     __shared__ __align__(8) uint64_t descB[2 * 2 * MAX_KSTEPS];   /* [stage][plane][q*nchunk + kk] */
 
     uint8_t *sA = smem;                                         /* [Q][LIMBS][nslab][128][16] */
     uint8_t *sB = smem + p.a_group_bytes;                       /* [2 stages][2 planes][nslab][R][16] */
     int *accbuf = reinterpret_cast<int *>(sB + 2 * (size_t)p.b_stage_bytes);   /* [64 columns][128 rows] recombined accumulators */
-    short *pcmbuf = reinterpret_cast<short *>(accbuf + TC_N * 128);             /* [64 columns][PCM_PITCH] int16 PCM of the tile */
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nslab = p.Kp >> 4, nchunk = p.Kp >> 5;
     const int g = blockIdx.x % p.G;                             /* channel group of this CTA */
-    const int t_first = blockIdx.x / p.G, t_step = gridDim.x / p.G;
+    const int chunk = blockIdx.x / p.G;
+    const long long k0 = (long long)chunk * p.L;                /* first output of this chunk */
+    const long long k1 = (k0 + p.L < p.K) ? k0 + p.L : p.K;     /* one past its last output */
+    const int my_tiles = (k0 < p.K) ? (int)((k1 - k0 + 8 + TC_N - 1) / TC_N) : 0;
 
     /* ---- one-time setup ---- */
     {
@@ -120,32 +165,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
 
     if (warp < XF_WARPS) {
         /* ================= transform: raw cs16 samples -> hi/lo byte planes of the smem ring =================
-         * Plane row m of tile t = stream samples [(t*63 + m - 1) * D, +D); item (m, j) is one 16-byte slab entry
-         * = 8 complex samples = 32 raw bytes.  Consecutive threads take consecutive j: 32-byte pieces of one
-         * contiguous run, so the global reads coalesce. */
+         * Plane row m of a tile whose column 0 is output kt0 = stream samples [(kt0 + m) * D, +D); item (m, j) is one
+         * 16-byte slab entry = 8 complex samples = 32 raw bytes.  Consecutive threads take consecutive j: 32-byte
+         * pieces of one contiguous run, so the global reads coalesce.  Entries past D in a row multiply zero taps, so
+         * the fast path does not mask them. */
         const int items = p.R * nslab;
         const uint32_t slab_bytes = (uint32_t)p.R * 16;
-        int it = 0;
-        for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
+        for (int it = 0; it < my_tiles; it++) {
             const int s = it & 1, ph = (it >> 1) & 1;
             if (tid == 0) DBG(0, it, 0);
-            ptx::mbar_wait(&b_empty[s], ph ^ 1);
+            ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1, 64);
             if (tid == 0) DBG(0, it, 1);
             uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
-            const long long row_base = (long long)t * TC_KP - 1;
-            for (int item = tid; item < items; item += XF_THREADS) {
-                const int m = item / nslab, j = item - m * nslab;
-                const long long s0 = (row_base + m) * (long long)p.D + 8 * j;
-                uint32_t w[8];
+            const long long row_base = k0 - 8 + (long long)it * TC_N;
+            const long long s_first = row_base * (long long)p.D;
+            const long long s_last = s_first + (long long)(p.R - 1) * p.D + 8 * nslab + 12;     /* one past the furthest word read */
+            if (s_first >= p.in.carry_len + 4 && s_last <= p.in.total) {
+                const int *base = p.in.fresh + (s_first - p.in.carry_len);
+#pragma unroll 2
+                for (int item = tid; item < items; item += XF_THREADS) {
+                    const int m = __float2int_rz(__fmul_rn((float)item + 0.5f, p.inv_nslab));
+                    const int j = item - m * nslab;
+                    uint32_t w[8];
+                    load8_unaligned(base + m * p.D + 8 * j, w);
+                    split_store(w, dst + (size_t)j * slab_bytes + m * 16, dst + (size_t)(nslab + j) * slab_bytes + m * 16);
+                }
+            } else {
+                for (int item = tid; item < items; item += XF_THREADS) {
+                    const int m = item / nslab, j = item - m * nslab;
+                    const long long s0 = (row_base + m) * (long long)p.D + 8 * j;
+                    uint32_t w[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) w[u] = (8 * j + u < p.D) ? (uint32_t)in_sample(p.in, s0 + u) : 0u;
-                uint4 lo, hi;       /* packed sample = bytes (lo(re), hi(re), lo(im), hi(im)) */
-                lo.x = __byte_perm(w[0], w[1], 0x6420); hi.x = __byte_perm(w[0], w[1], 0x7531);
-                lo.y = __byte_perm(w[2], w[3], 0x6420); hi.y = __byte_perm(w[2], w[3], 0x7531);
-                lo.z = __byte_perm(w[4], w[5], 0x6420); hi.z = __byte_perm(w[4], w[5], 0x7531);
-                lo.w = __byte_perm(w[6], w[7], 0x6420); hi.w = __byte_perm(w[6], w[7], 0x7531);
-                *reinterpret_cast<uint4 *>(dst + (size_t)j * slab_bytes + m * 16) = hi;
-                *reinterpret_cast<uint4 *>(dst + (size_t)(nslab + j) * slab_bytes + m * 16) = lo;
+                    for (int u = 0; u < 8; u++) w[u] = (8 * j + u < p.D) ? (uint32_t)in_sample(p.in, s0 + u) : 0u;
+                    split_store(w, dst + (size_t)j * slab_bytes + m * 16, dst + (size_t)(nslab + j) * slab_bytes + m * 16);
+                }
             }
             ptx::fence_proxy_async();       /* generic-proxy stores -> visible to the tensor core's async proxy */
             __syncwarp();
@@ -159,13 +212,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             const uint32_t id_su = ptx::idesc_i8(128, TC_N, true, false);   /* A s8, B u8 */
             const uint32_t id_us = ptx::idesc_i8(128, TC_N, false, true);
             const uint32_t id_uu = ptx::idesc_i8(128, TC_N, false, false);
-            int it = 0;
-            for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
+            for (int it = 0; it < my_tiles; it++) {
                 const int s = it & 1, ph = (it >> 1) & 1;
                 DBG(1, it, 0);
-                ptx::mbar_wait_sleep(&b_full[s], ph);
+                ptx::mbar_wait_sleep(&b_full[s], ph, 200000);
                 DBG(1, it, 1);
-                ptx::mbar_wait_sleep(&t_empty[s], ph ^ 1);
+                ptx::mbar_wait_sleep(&t_empty[s], ph ^ 1, 200000);
                 DBG(1, it, 2);
                 ptx::tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)s * 256;         /* slots: +0 (2^16), +64 (2^8), +128 (1) */
@@ -202,21 +254,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
         /* compute mapping: consecutive lanes = consecutive channels (conflict-free smem reads) */
         const int et = tid - 32 * EPI_WARP0;        /* 0 .. EPI_THREADS-1 */
         const int ch = et & 63;
-        const int r = et >> 6;                      /* TC_STEP-column range this thread turns into PCM */
-        const int c0 = TC_STEP * r;
+        const int r = et >> 6;                      /* which 8-column block of the tile this thread turns into PCM */
         const int c = g * TC_CH + ch;
         const bool live = c < p.C;
         const int iw = live ? __ldg(p.incr + c) : 0;
         const int i_re = lo16(iw), i_im = hi16(iw);
         const int2 *acc2 = reinterpret_cast<const int2 *>(accbuf);
-        int *const iq_c = p.iq_out ? p.iq_out + (size_t)c * p.pitch : nullptr;
-        const int K32 = (int)p.K;                   /* outputs per channel of one submit always fit 31 bits */
+        short *const pcm_c = p.pcm + (size_t)c * p.pitch;
+        int *const iq_c = KEEP_IQ ? p.iq_out + (size_t)c * p.pitch : nullptr;
+        AtanParams ap = p.atan;
+        ap.use_fma = FMA ? 1 : 0;
 
-        int it = 0;
-        for (int t = t_first; t < p.nr_tiles; t += t_step, it++) {
+        for (int it = 0; it < my_tiles; it++) {
             const int s = it & 1, ph = (it >> 1) & 1;
             if (et == 0) DBG(2, it, 0);
-            ptx::mbar_wait(&t_full[s], ph);
+            ptx::mbar_wait_sleep(&t_full[s], ph, 32);
             if (et == 0) DBG(2, it, 1);
             ptx::tc_fence_after();
             /* ---- phase 1: drain TMEM, recombine the limbs modulo 2^32, park in smem as [column][row] ---- */
@@ -239,64 +291,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      /* all 64 columns parked */
             if (et == 0) DBG(2, it, 3);
 
-            /* ---- phase 2: one channel x TC_STEP columns per thread ---- */
-            if (live) {
-                const int cwk = __ldg(p.ckpt + ((size_t)t * TC_SUB + r) * p.C + c);
+            /* ---- phase 2: one channel x 8 columns per thread ---- */
+            const long long kfirst = k0 - 8 + (long long)it * TC_N + 8 * r;     /* output index of this thread's first column */
+            int nvalid = (k1 - kfirst > 8) ? 8 : (int)(k1 - kfirst);
+            if (live && kfirst >= k0 && nvalid > 0) {
+                const int cwk = __ldg(p.ckpt + (((size_t)chunk * p.n_tiles + it) * TC_SUB + r) * p.C + c);
                 int r_re = lo16(cwk), r_im = hi16(cwk);
                 int p_re, p_im;
-                int col = c0;
-                if (r > 0 || t > 0) {
-                    /* previous output (column c0-1, or the tile's leading column 0): checkpoint is its phase */
-                    const int lead = (r > 0) ? c0 - 1 : 0;
-                    const int2 v = acc2[lead * 64 + ch];
-                    derotate(rq14(v.x), rq14(v.y), r_re, r_im, p_re, p_im);
-                    rot_step(r_re, r_im, i_re, i_im);
-                    if (r == 0) col = 1;
-                } else {
-                    /* very first column of the submit: y[k0-1] is carried state, checkpoint is column 1's phase */
+                if (r == 0) {
+                    /* the previous output is the last column of the previous tile; checkpoint = phase of column 0 */
+                    const int w = yprev_s[it & 1][ch];
+                    p_re = lo16(w); p_im = hi16(w);
+                } else if (kfirst == 0) {
+                    /* very first output of the submit: y[-1] is carried state; checkpoint = phase of output 0 */
                     const int lw = __ldg(p.last_in + c);
                     p_re = lo16(lw); p_im = hi16(lw);
-                    col = 1;
+                } else {
+                    /* previous output = column 8r-1 of this tile; the checkpoint is its phase */
+                    const int2 v = acc2[(8 * r - 1) * 64 + ch];
+                    derotate(rq14(v.x), rq14(v.y), r_re, r_im, p_re, p_im);
+                    rot_step(r_re, r_im, i_re, i_im);
                 }
-                const int kofs = t * TC_KP - 1;                         /* stream output index of column 0 */
-                int col_end = c0 + TC_STEP;
-                if (kofs + col_end > K32) col_end = K32 - kofs;         /* ragged last tile */
-                const bool produced = col < col_end;
-                const int2 *src = acc2 + col * 64 + ch;
-                short *out = pcmbuf + col * PCM_PITCH + ch;
-#pragma unroll 8
-                for (; col < col_end; col++, src += 64, out += PCM_PITCH) {
-                    const int2 v = *src;
+                const int2 *src = acc2 + (8 * r) * 64 + ch;
+                uint32_t out[4];
+                int l_re = 0, l_im = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int2 v = src[u * 64];
                     int y_re, y_im;
                     derotate(rq14(v.x), rq14(v.y), r_re, r_im, y_re, y_im);
                     rot_step(r_re, r_im, i_re, i_im);
-                    *out = (short)fm_pcm_bf(y_re, y_im, p_re, p_im, atan_s, p.atan);
-                    if (iq_c) iq_c[kofs + col] = pack16(y_re, y_im);
+                    const uint32_t pcm = (uint32_t)fm_pcm_bf(y_re, y_im, p_re, p_im, atan_s, ap) & 0xffffu;
+                    if (u & 1) out[u >> 1] |= pcm << 16; else out[u >> 1] = pcm;
+                    if (KEEP_IQ) { if (u < nvalid) iq_c[kfirst + u] = pack16(y_re, y_im); }
                     p_re = y_re; p_im = y_im;
+                    if (u == nvalid - 1) { l_re = y_re; l_im = y_im; }
+                }
+                if (r == TC_SUB - 1) yprev_s[(it + 1) & 1][ch] = pack16(p_re, p_im);
+                if (nvalid == 8) {
+                    *reinterpret_cast<uint4 *>(pcm_c + kfirst) = make_uint4(out[0], out[1], out[2], out[3]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (u < nvalid) pcm_c[kfirst + u] = (short)(out[u >> 1] >> (16 * (u & 1)));
                 }
                 /* the thread that produced the submit's last output hands y[K-1] to the next submit */
-                if (produced && kofs + col_end == K32) p.last_out[c] = pack16(p_re, p_im);
+                if (kfirst + nvalid == p.K) p.last_out[c] = pack16(l_re, l_im);
             }
             if (et == 0) DBG(2, it, 4);
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      /* accbuf free; the tile's PCM is complete in smem */
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");      /* accbuf may be overwritten by the next tile */
             if (et == 0) DBG(2, it, 5);
-            /* ---- phase 3: coalesced copy-out; warp e owns channels 4e..4e+3, lanes run along time ---- */
-            {
-                const int kofs = t * TC_KP - 1;
-                int ncol = K32 - kofs;                                  /* valid columns are 1 .. ncol-1 */
-                if (ncol > TC_N) ncol = TC_N;
-                const bool ok0 = lane >= 1 && lane < ncol, ok1 = lane + 32 < ncol;
-#pragma unroll
-                for (int j = 0; j < TC_CH / EPI_WARPS; j++) {
-                    const int chn = e * (TC_CH / EPI_WARPS) + j;
-                    const int cg = g * TC_CH + chn;
-                    if (cg < p.C) {
-                        short *dst = p.pcm + (size_t)cg * p.pitch + kofs;
-                        if (ok0) dst[lane] = pcmbuf[lane * PCM_PITCH + chn];
-                        if (ok1) dst[lane + 32] = pcmbuf[(lane + 32) * PCM_PITCH + chn];
-                    }
-                }
-            }
         }
     }
 
@@ -340,8 +384,8 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
     pl.limbs = fits8 ? 1 : 2;
     pl.a_group_bytes = (size_t)pl.Q * pl.limbs * pl.Kp * 128;
     pl.b_stage_bytes = (size_t)2 * pl.Kp * pl.R;
-    pl.smem_bytes = pl.a_group_bytes + 2 * pl.b_stage_bytes + (size_t)TC_N * 128 * 4 + (size_t)TC_N * 66 * 2 + 128;
-    const size_t static_smem = 5248 + 256;  /* atan table, descriptors, barriers */
+    pl.smem_bytes = pl.a_group_bytes + 2 * pl.b_stage_bytes + (size_t)TC_N * 128 * 4 + 128;
+    const size_t static_smem = 5248 + 512 + 256;  /* atan table, descriptors, previous-sample hand-off, barriers */
     if (pl.smem_bytes + static_smem > (size_t)smem_max) { pl.why = "tap image + sample ring exceed shared memory"; return pl; }
     if ((size_t)pl.R * 16 >= (1u << 18)) { pl.why = "tile too tall for the descriptor"; return pl; }
     if (pl.Q * (pl.Kp / 32) > 64) { pl.why = "too many K steps (taps / decimation too large)"; return pl; }
@@ -373,32 +417,58 @@ void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_
                 }
 }
 
-cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, int nr_sms, cudaStream_t st)
+TcGeom tc_geometry(const TcPlan &pl, long long K, int nr_sms)
 {
+    TcGeom gm;
+    long long chunks = nr_sms / pl.G;
+    if (chunks < 1) chunks = 1;
+    if (K <= 0) { gm.chunks = 0; gm.n_tiles = 0; gm.L = TC_N - 8; return gm; }
+    const long long per = (K + chunks - 1) / chunks;
+    gm.n_tiles = (int)((per + 8 + TC_N - 1) / TC_N);
+    gm.L = (long long)TC_N * gm.n_tiles - 8;
+    gm.chunks = (int)((K + gm.L - 1) / gm.L);
+    return gm;
+}
+
+size_t tc_max_ckpt_tiles(const TcPlan &pl, long long max_K, int nr_sms)
+{
+    long long chunks = nr_sms / pl.G;
+    if (chunks < 1) chunks = 1;
+    return (size_t)(max_K / TC_N + 2 * chunks + 2);
+}
+
+template <int LIMBS, bool KEEP_IQ, bool FMA>
+static cudaError_t launch_variant(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(tc_fir_fm_kernel<LIMBS, KEEP_IQ, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tc_fir_fm_kernel<LIMBS, KEEP_IQ, FMA><<<ctas, TC_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st)
+{
+    if (b.geom.chunks <= 0) return cudaSuccess;
     TcKernelParams p;
     p.in = b.in; p.D = pl.D;
     p.tap_img = b.tap_img; p.incr = b.incr; p.ckpt = b.ckpt; p.last_in = b.last_in; p.last_out = b.last_out;
-    p.atan_tab = b.atan_tab; p.pcm = b.pcm; p.iq_out = b.iq_out; p.pitch = b.pitch; p.K = b.K;
-    p.nr_tiles = b.nr_tiles; p.C = pl.C; p.G = pl.G; p.Kp = pl.Kp; p.Q = pl.Q; p.R = pl.R;
+    p.atan_tab = b.atan_tab; p.pcm = b.pcm; p.iq_out = b.iq_out; p.pitch = b.pitch; p.K = (long long)b.K;
+    p.L = b.geom.L; p.n_tiles = b.geom.n_tiles;
+    p.C = pl.C; p.G = pl.G; p.Kp = pl.Kp; p.Q = pl.Q; p.R = pl.R;
+    p.inv_nslab = 1.0f / (float)(pl.Kp / 16);
     p.a_group_bytes = (uint32_t)pl.a_group_bytes; p.b_stage_bytes = (uint32_t)pl.b_stage_bytes;
     p.atan = b.atan;
     p.dbg = b.dbg;
-    /* persistent grid: a multiple of G CTAs, at most one per SM, no more CTAs than (group, tile) pairs */
-    long long ctas = (long long)(nr_sms / pl.G) * pl.G;
-    if (ctas < pl.G) ctas = pl.G;
-    const long long work = (long long)pl.G * b.nr_tiles;
-    if (ctas > work) ctas = work;
-    cudaError_t e;
+    /* persistent grid: one CTA per (chunk, channel group), at most one per SM */
+    const unsigned ctas = (unsigned)b.geom.chunks * (unsigned)pl.G;
+    const bool iq = b.iq_out != nullptr, fma = b.atan.use_fma != 0;
+    const size_t sm = pl.smem_bytes;
     if (pl.limbs == 2) {
-        e = cudaFuncSetAttribute(tc_fir_fm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
-        if (e != cudaSuccess) return e;
-        tc_fir_fm_kernel<2><<<(unsigned)ctas, TC_THREADS, pl.smem_bytes, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(tc_fir_fm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
-        if (e != cudaSuccess) return e;
-        tc_fir_fm_kernel<1><<<(unsigned)ctas, TC_THREADS, pl.smem_bytes, st>>>(p);
+        if (iq) return fma ? launch_variant<2, true, true>(p, ctas, sm, st) : launch_variant<2, true, false>(p, ctas, sm, st);
+        return fma ? launch_variant<2, false, true>(p, ctas, sm, st) : launch_variant<2, false, false>(p, ctas, sm, st);
     }
-    return cudaGetLastError();
+    if (iq) return fma ? launch_variant<1, true, true>(p, ctas, sm, st) : launch_variant<1, true, false>(p, ctas, sm, st);
+    return fma ? launch_variant<1, false, true>(p, ctas, sm, st) : launch_variant<1, false, false>(p, ctas, sm, st);
 }
 
 } // namespace tslb200

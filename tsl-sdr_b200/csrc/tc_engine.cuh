@@ -8,8 +8,8 @@
 
 namespace tslb200 {
 
-constexpr int TC_N  = 64;               /* FIR outputs (columns) per tile: 1 leading + 63 PCM outputs */
-constexpr int TC_KP = TC_N - 1;         /* PCM outputs per tile */
+constexpr int TC_N  = 64;               /* FIR outputs (columns) per tile */
+constexpr int TC_LEAD = 8;              /* columns at the head of a chunk that only provide the discriminator's previous sample */
 constexpr int TC_STEP = 8;              /* columns one epilogue thread turns into PCM */
 constexpr int TC_SUB = TC_N / TC_STEP;  /* derotator checkpoints per tile (one per TC_STEP columns) */
 constexpr int TC_CH = 64;               /* channels per CTA (128 accumulator rows: re/im interleaved) */
@@ -32,6 +32,16 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
 /* tap image for all groups: [G][Q][limbs][Kp/16][128][16] bytes */
 void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_im, std::vector<uint8_t> &img);
 
+/* How the K outputs of one submit are cut up: `chunks` contiguous ranges of L = TC_N * n_tiles - TC_LEAD outputs
+ * (one CTA per range and channel group); tile i of chunk j covers outputs j*L - TC_LEAD + TC_N*i + [0, TC_N). */
+struct TcGeom {
+    int chunks = 0;
+    int n_tiles = 0;
+    long long L = 0;
+};
+TcGeom tc_geometry(const TcPlan &pl, long long K, int nr_sms);
+size_t tc_max_ckpt_tiles(const TcPlan &pl, long long max_K, int nr_sms);
+
 struct TcBatch {
     InWindow in;
     const uint8_t *tap_img;
@@ -42,11 +52,11 @@ struct TcBatch {
     int *iq_out;
     long long pitch;
     unsigned long long K;
-    int nr_tiles;
+    TcGeom geom;
     AtanParams atan;
     long long *dbg = nullptr;
 };
 
-cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, int nr_sms, cudaStream_t st);
+cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st);
 
 } // namespace tslb200

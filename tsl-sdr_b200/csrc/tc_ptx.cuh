@@ -49,12 +49,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) { }
 }
 /* for the single-lane producer / MMA roles: do not burn issue slots the epilogue warps need */
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t hint_ns = 200000u)
 {
     uint32_t ok = 0;
     while (!ok) {       /* try_wait with a suspend-time hint: the warp sleeps in hardware until the phase flips */
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(200000u) : "memory");
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
     }
 }
 
