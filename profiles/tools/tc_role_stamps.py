@@ -1,6 +1,6 @@
 import os, sys, numpy as np
 os.environ["GPUCHAN_DEBUG_STAMPS"]="1"
-sys.path.insert(0,'/root/repo'); import tslb200_loader; tslb200_loader.load_package()
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))); import tslb200_loader; tslb200_loader.load_package()
 from tsl_sdr_b200 import synth
 from tsl_sdr_b200.gpuchan import GpuChan
 import ctypes as C

@@ -796,6 +796,7 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
             tb.atan_tab = h->d_atan; tb.pcm = h->d_pcm[slot]; tb.iq_out = h->d_iq[slot]; tb.pitch = (long long)h->pitch;
             tb.K = K; tb.geom = tg; tb.atan = h->atan;
             tb.dbg = h->d_dbg;
+            tb.dbg_flags = (h->d_dbg && getenv("GPUCHAN_DEBUG_SKIP")) ? atoi(getenv("GPUCHAN_DEBUG_SKIP")) : 0;
             CUDA_TRY(tc_launch_fir_fm(h->tc, tb, st));
             h->launches++;
         } else {

@@ -37,8 +37,12 @@ namespace {
 constexpr int EPI_WARPS = 16;
 constexpr int XF_WARPS = 4;             /* transform warps: raw cs16 -> byte planes in smem */
 constexpr int XF_THREADS = 32 * XF_WARPS;
-constexpr int MMA_WARP = XF_WARPS;      /* warp index of the MMA issuer */
-constexpr int EPI_WARP0 = XF_WARPS + 1; /* first epilogue warp (EPI_WARP0 % 4 == 1: any 4 consecutive warps cover all TMEM slices) */
+/* Warp roles, lowest warp index first: epilogue | transform | MMA issuer.  The SM's warp arbiter favours the highest
+ * warp index, so the short, latency-critical roles (MMA issue, then the loads feeding it) sit on top and are never
+ * starved by the 16 arithmetic-heavy epilogue warps. */
+constexpr int EPI_WARP0 = 0;            /* first epilogue warp; any 4 consecutive warps cover all 4 TMEM lane slices */
+constexpr int XF_WARP0 = EPI_WARPS;     /* first transform warp */
+constexpr int MMA_WARP = EPI_WARPS + XF_WARPS;      /* warp index of the MMA issuer */
 constexpr int TC_THREADS = 32 * (XF_WARPS + 1 + EPI_WARPS);
 constexpr int MAX_KSTEPS = 64;          /* Q * (Kp/32) descriptors kept in shared memory */
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
@@ -62,6 +66,7 @@ struct TcKernelParams {
     uint32_t a_group_bytes, b_stage_bytes;
     AtanParams atan;
     long long *dbg;         /* optional per-role clock stamps of CTA 0 (bench diagnostics) */
+    int dbg_flags;          /* diagnostics only: 1 = skip the epilogue arithmetic, 2 = skip the transform */
 };
 
 /* 8 consecutive raw samples starting at a (4-byte aligned, inside the fresh buffer with >= 12 samples of slack):
@@ -112,13 +117,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
     __shared__ uint32_t tmem_base_s;
     __shared__ float2 atan_s[256];
     __shared__ int yprev_s[2][TC_CH];
-    __shared__ __align__(8) uint64_t descA[MAX_KSTEPS * 2];       /* [q*nchunk + kk][limb] */
-    __shared__ __align__(8) uint64_t descB[2 * 2 * MAX_KSTEPS];   /* [stage][plane][q*nchunk + kk] */
 
     uint8_t *sA = smem;                                         /* [Q][LIMBS][nslab][128][16] */
     uint8_t *sB = smem + p.a_group_bytes;                       /* [2 stages][2 planes][nslab][R][16] */
     int *accbuf = reinterpret_cast<int *>(sB + 2 * (size_t)p.b_stage_bytes);   /* [64 columns][128 rows] recombined accumulators */
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);       /* same value, but provably warp-uniform for the compiler */
     const int nslab = p.Kp >> 4, nchunk = p.Kp >> 5;
     const int g = blockIdx.x % p.G;                             /* channel group of this CTA */
     const int chunk = blockIdx.x / p.G;
@@ -141,21 +145,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
         ptx::fence_mbar_init();
     }
     if (warp == MMA_WARP) ptx::tmem_alloc(&tmem_base_s, 512);
-    {   /* operand descriptors are tile-invariant: build them once */
-        const uint32_t a_mat_bytes = (uint32_t)p.Kp * 128, slab_bytes = (uint32_t)p.R * 16;
-        const int nsteps = p.Q * nchunk;
-        for (int i = tid; i < nsteps * 2; i += TC_THREADS) {
-            const int step = i >> 1, limb = i & 1, q = step / nchunk, kk = step - q * nchunk;
-            if (limb < LIMBS)
-                descA[i] = ptx::smem_desc_kmajor_noswz(ptx::smem_u32(sA) + (uint32_t)(q * LIMBS + limb) * a_mat_bytes + kk * 2 * 2048, 2048, 128);
-        }
-        for (int i = tid; i < nsteps * 4; i += TC_THREADS) {
-            const int step = i % nsteps, pl = (i / nsteps) & 1, st = i / (2 * nsteps);
-            const int q = step / nchunk, kk = step - q * nchunk;
-            const uint32_t base = ptx::smem_u32(sB) + (uint32_t)st * p.b_stage_bytes + (uint32_t)pl * nslab * slab_bytes;
-            descB[(st * 2 + pl) * MAX_KSTEPS + step] = ptx::smem_desc_kmajor_noswz(base + kk * 2 * slab_bytes + q * 16, slab_bytes, 128);
-        }
-    }
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
     __syncthreads();
@@ -163,7 +152,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
     const uint32_t tmem_base = tmem_base_s;
 #define DBG(role, it, slot) do { if (p.dbg && blockIdx.x == 0 && (it) < 32) p.dbg[((role) * 32 + (it)) * 8 + (slot)] = clock64(); } while (0)
 
-    if (warp < XF_WARPS) {
+    if (warp >= XF_WARP0 && warp < XF_WARP0 + XF_WARPS) {
+        const int xt = tid - 32 * XF_WARP0;         /* 0 .. XF_THREADS-1 */
         /* ================= transform: raw cs16 samples -> hi/lo byte planes of the smem ring =================
          * Plane row m of a tile whose column 0 is output kt0 = stream samples [(kt0 + m) * D, +D); item (m, j) is one
          * 16-byte slab entry = 8 complex samples = 32 raw bytes.  Consecutive threads take consecutive j: 32-byte
@@ -171,19 +161,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
          * the fast path does not mask them. */
         const int items = p.R * nslab;
         const uint32_t slab_bytes = (uint32_t)p.R * 16;
+        /* L2 prefetch of the TC_N new block-rows of tile `t` (the stream is read exactly once, straight from HBM) */
+        auto prefetch_tile = [&](int t) {
+            if (t >= my_tiles) return;
+            const long long s_a = (k0 - 8 + (long long)t * TC_N + (p.Q - 1)) * (long long)p.D - p.in.carry_len;
+            long long s_b = s_a + (long long)TC_N * p.D;
+            const long long n_fresh = p.in.total - p.in.carry_len;
+            if (s_a < 0 || s_a >= n_fresh) return;
+            if (s_b > n_fresh) s_b = n_fresh;
+            const uintptr_t a = reinterpret_cast<uintptr_t>(p.in.fresh + s_a) & ~(uintptr_t)15;
+            const uintptr_t b = reinterpret_cast<uintptr_t>(p.in.fresh + s_b) & ~(uintptr_t)15;
+            if (b > a) ptx::prefetch_l2(reinterpret_cast<const void *>(a), (uint32_t)(b - a));
+        };
+        if (xt == 0) { prefetch_tile(1); prefetch_tile(2); }
         for (int it = 0; it < my_tiles; it++) {
             const int s = it & 1, ph = (it >> 1) & 1;
-            if (tid == 0) DBG(0, it, 0);
+            if (xt == 0) { DBG(0, it, 0); prefetch_tile(it + 3); }
             ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1, 64);
-            if (tid == 0) DBG(0, it, 1);
+            if (xt == 0) DBG(0, it, 1);
             uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
             const long long row_base = k0 - 8 + (long long)it * TC_N;
             const long long s_first = row_base * (long long)p.D;
             const long long s_last = s_first + (long long)(p.R - 1) * p.D + 8 * nslab + 12;     /* one past the furthest word read */
-            if (s_first >= p.in.carry_len + 4 && s_last <= p.in.total) {
+            if (p.dbg_flags & 2) {
+            } else if (s_first >= p.in.carry_len + 4 && s_last <= p.in.total) {
                 const int *base = p.in.fresh + (s_first - p.in.carry_len);
 #pragma unroll 2
-                for (int item = tid; item < items; item += XF_THREADS) {
+                for (int item = xt; item < items; item += XF_THREADS) {
                     const int m = __float2int_rz(__fmul_rn((float)item + 0.5f, p.inv_nslab));
                     const int j = item - m * nslab;
                     uint32_t w[8];
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
                     split_store(w, dst + (size_t)j * slab_bytes + m * 16, dst + (size_t)(nslab + j) * slab_bytes + m * 16);
                 }
             } else {
-                for (int item = tid; item < items; item += XF_THREADS) {
+                for (int item = xt; item < items; item += XF_THREADS) {
                     const int m = item / nslab, j = item - m * nslab;
                     const long long s0 = (row_base + m) * (long long)p.D + 8 * j;
                     uint32_t w[8];
@@ -203,46 +207,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             ptx::fence_proxy_async();       /* generic-proxy stores -> visible to the tensor core's async proxy */
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&b_full[s]);
-            if (tid == 0) DBG(0, it, 2);
+            if (xt == 0) DBG(0, it, 2);
         }
-    } else if (warp == MMA_WARP) {
-        /* ================= MMA issuer ================= */
-        if (lane == 0) {
-            const uint32_t id_ss = ptx::idesc_i8(128, TC_N, true, true);    /* A s8, B s8 */
-            const uint32_t id_su = ptx::idesc_i8(128, TC_N, true, false);   /* A s8, B u8 */
-            const uint32_t id_us = ptx::idesc_i8(128, TC_N, false, true);
-            const uint32_t id_uu = ptx::idesc_i8(128, TC_N, false, false);
-            for (int it = 0; it < my_tiles; it++) {
-                const int s = it & 1, ph = (it >> 1) & 1;
-                DBG(1, it, 0);
-                ptx::mbar_wait_sleep(&b_full[s], ph, 200000);
-                DBG(1, it, 1);
-                ptx::mbar_wait_sleep(&t_empty[s], ph ^ 1, 200000);
-                DBG(1, it, 2);
-                ptx::tc_fence_after();
-                const uint32_t acc = tmem_base + (uint32_t)s * 256;         /* slots: +0 (2^16), +64 (2^8), +128 (1) */
-                const uint64_t *dbh_p = descB + (s * 2 + 0) * MAX_KSTEPS, *dbl_p = descB + (s * 2 + 1) * MAX_KSTEPS;
-                const int nsteps = p.Q * nchunk;
-                for (int st = 0; st < nsteps; st++) {
-                    const uint64_t dbh = dbh_p[st], dbl = dbl_p[st];
-                    const uint32_t accum = st > 0;
-                    if (LIMBS == 2) {
-                        const uint64_t dal = descA[2 * st], dah = descA[2 * st + 1];
-                        ptx::mma_i8(acc + 0,   dah, dbh, id_ss, accum);
-                        ptx::mma_i8(acc + 64,  dah, dbl, id_su, accum);
-                        ptx::mma_i8(acc + 64,  dal, dbh, id_us, 1);
-                        ptx::mma_i8(acc + 128, dal, dbl, id_uu, accum);
-                    } else {
-                        const uint64_t da = descA[2 * st];
-                        ptx::mma_i8(acc + 64,  da, dbh, id_ss, accum);
-                        ptx::mma_i8(acc + 128, da, dbl, id_su, accum);
+    } else if (warp_u == MMA_WARP) {
+        /* ================= MMA issuer =================
+         * The whole warp walks the (warp-uniform) loops so that descriptors live in uniform registers; only the
+         * tcgen05 instructions themselves are issued by one lane. */
+        const bool leader = lane == 0;
+        const uint32_t id_ss = ptx::idesc_i8(128, TC_N, true, true);    /* A s8, B s8 */
+        const uint32_t id_su = ptx::idesc_i8(128, TC_N, true, false);   /* A s8, B u8 */
+        const uint32_t id_us = ptx::idesc_i8(128, TC_N, false, true);
+        const uint32_t id_uu = ptx::idesc_i8(128, TC_N, false, false);
+        const uint32_t slab16 = (uint32_t)p.R;                           /* slab_bytes >> 4 */
+        const uint32_t a_mat16 = (uint32_t)p.Kp * 8;                     /* a_mat_bytes >> 4 */
+        const uint64_t descA0 = ptx::smem_desc_kmajor_noswz(ptx::smem_u32(sA), 2048, 128);
+        const uint64_t descB0 = ptx::smem_desc_kmajor_noswz(ptx::smem_u32(sB), slab16 * 16, 128);
+        for (int it = 0; it < my_tiles; it++) {
+            const int s = it & 1, ph = (it >> 1) & 1;
+            if (leader) DBG(1, it, 0);
+            ptx::mbar_wait_sleep(&b_full[s], ph, 200000);
+            if (leader) DBG(1, it, 1);
+            ptx::mbar_wait_sleep(&t_empty[s], ph ^ 1, 200000);
+            if (leader) DBG(1, it, 2);
+            ptx::tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)s * 256;         /* slots: +0 (2^16), +64 (2^8), +128 (1) */
+            const uint64_t dB_hi0 = descB0 + (uint64_t)(((uint32_t)s * p.b_stage_bytes) >> 4);
+            const uint64_t dB_lo0 = dB_hi0 + (uint64_t)((uint32_t)nslab * slab16);
+            uint32_t accum = 0;
+            for (int q = 0; q < p.Q; q++) {
+                const uint64_t dA_q = descA0 + (uint64_t)((uint32_t)(q * LIMBS) * a_mat16);
+                for (int kk = 0; kk < nchunk; kk++) {
+                    const uint64_t dal = dA_q + (uint64_t)((uint32_t)kk * 256u);         /* 2 slabs of 128 x 16 B */
+                    const uint64_t dbh = dB_hi0 + (uint64_t)((uint32_t)kk * 2u * slab16 + (uint32_t)q);
+                    const uint64_t dbl = dB_lo0 + (uint64_t)((uint32_t)kk * 2u * slab16 + (uint32_t)q);
+                    if (leader) {
+                        if (LIMBS == 2) {
+                            const uint64_t dah = dal + (uint64_t)a_mat16;
+                            ptx::mma_i8(acc + 0,   dah, dbh, id_ss, accum);
+                            ptx::mma_i8(acc + 64,  dah, dbl, id_su, accum);
+                            ptx::mma_i8(acc + 64,  dal, dbh, id_us, 1);
+                            ptx::mma_i8(acc + 128, dal, dbl, id_uu, accum);
+                        } else {
+                            ptx::mma_i8(acc + 64,  dal, dbh, id_ss, accum);
+                            ptx::mma_i8(acc + 128, dal, dbl, id_su, accum);
+                        }
                     }
+                    accum = 1;
                 }
+            }
+            if (leader) {
                 DBG(1, it, 3);
                 ptx::mma_commit(&b_empty[s]);       /* smem stage may be refilled once these MMAs have read it */
                 ptx::mma_commit(&t_full[s]);        /* accumulators complete */
                 DBG(1, it, 4);
             }
+            __syncwarp();
         }
     } else {
         /* ================= epilogue: TMEM -> smem -> derotate -> discriminate -> PCM ================= */
@@ -294,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const TcKernel
             /* ---- phase 2: one channel x 8 columns per thread ---- */
             const long long kfirst = k0 - 8 + (long long)it * TC_N + 8 * r;     /* output index of this thread's first column */
             int nvalid = (k1 - kfirst > 8) ? 8 : (int)(k1 - kfirst);
-            if (live && kfirst >= k0 && nvalid > 0) {
+            if (live && kfirst >= k0 && nvalid > 0 && !(p.dbg_flags & 1)) {
                 const int cwk = __ldg(p.ckpt + (((size_t)chunk * p.n_tiles + it) * TC_SUB + r) * p.C + c);
                 int r_re = lo16(cwk), r_im = hi16(cwk);
                 int p_re, p_im;
@@ -459,6 +478,7 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     p.a_group_bytes = (uint32_t)pl.a_group_bytes; p.b_stage_bytes = (uint32_t)pl.b_stage_bytes;
     p.atan = b.atan;
     p.dbg = b.dbg;
+    p.dbg_flags = b.dbg_flags;
     /* persistent grid: one CTA per (chunk, channel group), at most one per SM */
     const unsigned ctas = (unsigned)b.geom.chunks * (unsigned)pl.G;
     const bool iq = b.iq_out != nullptr, fma = b.atan.use_fma != 0;

@@ -55,6 +55,7 @@ struct TcBatch {
     TcGeom geom;
     AtanParams atan;
     long long *dbg = nullptr;
+    int dbg_flags = 0;
 };
 
 cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st);

@@ -65,6 +65,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+/* ask L2 to fetch [p, p + bytes) (16-byte aligned, multiple of 16) ahead of the loads that will want it */
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 /* ---- TMEM ---- */
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)     /* whole warp, ncols = 2^k >= 32 */
 {
