@@ -10,6 +10,13 @@
 #include <vector>
 using namespace tslb200;
 
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 struct Case { int N, nacc, a_adv16, b_adv16, sw, nmma, a_rows16 /* LBO of A >> 4 */, b_lbo16, twice_mid; };
 
 __global__ void __launch_bounds__(128, 1) mb_kernel(Case c, int reps, long long *out)
@@ -37,7 +44,7 @@ __global__ void __launch_bounds__(128, 1) mb_kernel(Case c, int reps, long long 
                 const uint64_t da = dA0 + (uint64_t)((uint32_t)((i >> 2) & 3) * c.a_adv16);
                 const uint64_t db = dB0 + (uint64_t)((uint32_t)((i >> 2) & 3) * c.b_adv16);
                 const uint32_t i1 = c.sw ? id1 : id0;
-                if (tid == 0) {
+                if (elect_one()) {
                     ptx::mma_i8(tmem + s0, da, db, id0, 1);
                     ptx::mma_i8(tmem + s1, da, db + 1, i1, 1);
                     ptx::mma_i8(tmem + s2, da + c.a_adv16, db, id0, 1);
@@ -72,6 +79,10 @@ int main()
         { 256, 1, 256, 130, 0, 64, 128, 257, 0 }, /* N = 256 */
         { 256, 2, 256, 130, 0, 64, 128, 257, 0 },
         { 32, 1, 256, 130, 0, 64, 128, 65, 0 },
+        { 80, 1, 256, 162, 0, 64, 128, 81, 0 },
+        { 80, 2, 256, 162, 0, 64, 128, 81, 0 },
+        { 96, 2, 256, 162, 0, 64, 128, 97, 0 },
+        { 112, 2, 256, 162, 0, 64, 128, 113, 0 },
         { 64, 1, 256, 130, 0, 64, 128, 64, 0 },   /* B slab stride a multiple of 128 B */
         { 64, 1, 256, 130, 0, 64, 128, 72, 0 },
     };

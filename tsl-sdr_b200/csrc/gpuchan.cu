@@ -151,15 +151,12 @@ __global__ void rot_cycle_detect_kernel(const int *__restrict__ incr, int nr_cha
  * IMAD engine (mode 0): tile t covers FIR outputs (columns) j = 0..KT-1 <-> output t*KP - 1 + j (KP = KT-1); column
  *   0 only feeds the discriminator's "previous sample".  r = 0 is the phase of column 0 (column 1 for the first tile
  *   of a submit, whose column 0 is the previous submit's last output), r > 0 the phase of column step*r-1.
- * Tensor-core engine (mode 1): tile t = chunk j * n + i covers outputs j*L - 8 + 64*i + [0, 64) (tc_engine.cuh).
- *   r > 0: phase of column 8r-1, the previous sample of sub-block r (clamped to output 0 for the very first output
- *   of the submit, whose previous sample is carried state); r = 0: phase of column 0 (its previous sample crosses
- *   tiles through shared memory); unused for the first tile of a chunk, whose first 8 columns are lead-in. */
+ * Tensor-core engine (mode 1): tile t turns outputs 64*t + [0, 64) into PCM, 8 per thread (tc_engine.cuh); entry r
+ *   is the phase of output 64*t + 8*r - 1, the previous sample of block r (clamped to output 0 for the very first
+ *   output of the submit, whose previous sample is carried state). */
 struct CkptGeom {
     int mode;
     int KP, sub, step;      /* mode 0 */
-    int n;                  /* mode 1: tiles per chunk */
-    long long L;            /* mode 1: outputs per chunk */
 };
 
 __device__ __forceinline__ long long ckpt_local(const CkptGeom &gm, int t, int r)
@@ -168,9 +165,7 @@ __device__ __forceinline__ long long ckpt_local(const CkptGeom &gm, int t, int r
         const long long col = (r == 0) ? 0 : gm.step * r - 1;
         return (long long)t * gm.KP + col - 1 + ((t == 0 && r == 0) ? 1 : 0);
     }
-    const int j = t / gm.n, i = t - j * gm.n;
-    if (r == 0 && i == 0) return -1;
-    const long long v = (long long)j * gm.L - 8 + 64LL * i + (r == 0 ? 0 : 8 * r - 1);
+    const long long v = (long long)TC_OUT * t + TC_STEP * r - 1;
     return v < 0 ? 0 : v;
 }
 
@@ -742,8 +737,8 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
     int nr_tiles;
     if (use_tc) {
         tg = tc_geometry(h->tc, (long long)K, h->nr_sms);
-        cg.mode = 1; cg.sub = TC_SUB; cg.n = tg.n_tiles > 0 ? tg.n_tiles : 1; cg.L = tg.L;
-        nr_tiles = tg.chunks * tg.n_tiles;
+        cg.mode = 1; cg.sub = TC_SUB;
+        nr_tiles = tg.total_tiles;
     } else {
         cg.mode = 0; cg.KP = FIR_WARPS * h->R - 1; cg.sub = 1; cg.step = 16;
         nr_tiles = (int)((K + cg.KP - 1) / cg.KP);

@@ -8,11 +8,26 @@
 
 namespace tslb200 {
 
-constexpr int TC_N  = 64;               /* FIR outputs (columns) per tile */
-constexpr int TC_LEAD = 8;              /* columns at the head of a chunk that only provide the discriminator's previous sample */
-constexpr int TC_STEP = 8;              /* columns one epilogue thread turns into PCM */
-constexpr int TC_SUB = TC_N / TC_STEP;  /* derotator checkpoints per tile (one per TC_STEP columns) */
-constexpr int TC_CH = 64;               /* channels per CTA (128 accumulator rows: re/im interleaved) */
+constexpr int TC_OUT  = 64;             /* PCM outputs (columns that are turned into PCM) per tile */
+constexpr int TC_LEAD = 16;             /* columns computed ahead of them; only the last one is used (the discriminator's
+                                           previous sample), 16 because M = 128 MMAs need N % 16 == 0 */
+constexpr int TC_N    = TC_OUT + TC_LEAD;   /* FIR outputs (MMA N) per tile */
+constexpr int TC_STEP = 8;              /* consecutive outputs one epilogue thread turns into PCM (one 16-byte store) */
+constexpr int TC_SUB  = TC_OUT / TC_STEP;   /* derotator checkpoints per tile (one per TC_STEP outputs) */
+constexpr int TC_CH   = 64;             /* channels per CTA (128 accumulator rows) */
+constexpr int TC_ACC_STRIDE = TC_N;     /* TMEM columns between the limb accumulators of one stage */
+constexpr int TC_PROG_MAX = 160;        /* MMA instructions per tile the kernel parameter block can describe */
+
+enum { TC_MODE_SUM = 0, TC_MODE_RADIX = 1 };
+
+/* One tcgen05.mma of the per-tile program, packed for cheap decoding on the uniform datapath:
+ *   w0 = a_off16 (bits 0-13: tap-image offset of the 128 x 32 B chunk, in 16-byte units)
+ *      | b_off16 (bits 14-26: sample-stage offset of the (plane, K chunk, row shift), in 16-byte units)
+ *      | accumulate (bit 27: 0 for the first MMA into an accumulator) | accumulator index (bits 28-29)
+ *   w1 = the kind::i8 instruction descriptor (operand signedness, M, N) */
+struct TcMma {
+    uint32_t w0, w1;
+};
 
 struct TcPlan {
     bool ok = false;
@@ -20,24 +35,32 @@ struct TcPlan {
     int T = 0, D = 0, C = 0;
     int Kp = 0;                         /* bytes per block-row per plane: round_up(2*D, 32) */
     int Q = 0;                          /* block-rows spanned by the filter: ceil(T / D) */
-    int limbs = 2;                      /* 1 when every tap entry fits in int8 */
     int R = 0;                          /* plane rows per tile: TC_N + Q - 1 */
     int G = 0;                          /* channel groups of TC_CH */
+    int mode = TC_MODE_RADIX;           /* how int16 taps are made of int8 operands */
+    int accs = 3;                       /* limb accumulators per TMEM stage (SUM: 2, RADIX: 3) */
+    int nb_stages = 2;                  /* sample stages in shared memory */
+    int nt_stages = 2;                  /* accumulator stages in TMEM */
+    int a_chunks = 0;                   /* 4 KB chunks in one group's tap image */
     size_t a_group_bytes = 0;           /* bytes of one group's tap image */
     size_t b_stage_bytes = 0;           /* bytes of one sample tile (both planes) */
     size_t smem_bytes = 0;
+    std::vector<TcMma> prog;            /* the MMAs of one tile, in issue order */
+    /* tap image construction: for image chunk i, which (q, kk) it covers and which limb/term it holds */
+    struct Chunk { int q, kk, term; };
+    std::vector<Chunk> chunks;
 };
 
 TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_im, int smem_max);
-/* tap image for all groups: [G][Q][limbs][Kp/16][128][16] bytes */
+/* tap image for all groups: [G][a_chunks][2 slabs][128 rows][16] bytes */
 void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_im, std::vector<uint8_t> &img);
 
-/* How the K outputs of one submit are cut up: `chunks` contiguous ranges of L = TC_N * n_tiles - TC_LEAD outputs
- * (one CTA per range and channel group); tile i of chunk j covers outputs j*L - TC_LEAD + TC_N*i + [0, TC_N). */
+/* How the K outputs of one submit are cut up: tile t covers outputs TC_OUT*t + [0, TC_OUT) (plus TC_LEAD lead-in
+ * columns before them); CTA j of a channel group walks tiles [j * n_tiles, (j + 1) * n_tiles). */
 struct TcGeom {
-    int chunks = 0;
-    int n_tiles = 0;
-    long long L = 0;
+    int chunks = 0;                     /* CTAs per channel group */
+    int n_tiles = 0;                    /* tiles per CTA */
+    int total_tiles = 0;
 };
 TcGeom tc_geometry(const TcPlan &pl, long long K, int nr_sms);
 size_t tc_max_ckpt_tiles(const TcPlan &pl, long long max_K, int nr_sms);

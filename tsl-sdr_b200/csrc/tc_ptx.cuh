@@ -15,6 +15,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+/* exactly one lane of the (converged) warp gets true; lets the compiler issue tcgen05 instructions straight from
+ * uniform registers instead of looping over the active lanes */
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 /* ---- mbarrier ---- */
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
