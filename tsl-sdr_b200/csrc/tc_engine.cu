@@ -12,9 +12,9 @@
  * int8 pieces; the int32 partial accumulators are recombined modulo 2^32 in the epilogue, which is bit-identical
  * to the reference's wrapping int32 sum.  Samples are always split by radix (x = 256*hi + lo, hi signed, lo
  * unsigned).  Taps are split either
- *   SUM   (every |tap entry| <= 254, the usual narrow low-pass): v = v1 + v2 with both terms in int8; v2 is non-zero
- *         only around the centre of the filter, so only those K chunks issue a second pair of MMAs; two accumulators
- *         (weights 2^8 and 1) per tile, or
+ *   SUM   (every |tap entry| <= 508, the usual narrow low-pass): v = v1 + v2 (+ v3 + v4) with every term in int8; the
+ *         later terms are non-zero only around the centre of the filter, so only those K chunks issue further pairs
+ *         of MMAs; two accumulators (weights 2^8 and 1) per tile, or
  *   RADIX (any int16 taps): v = 256*hi + lo, four products per K chunk into three accumulators (2^16, 2^8, 1).
  * Only the K chunks a block-row really covers are issued (the last block-row of the filter is usually short).
  *
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         int s = 0, ph = 0;
         for (int it = 0; it < my_tiles; it++) {
             if (xt == 0) { DBG(0, it, 0); prefetch_tile(tile0 + it + 3); }
-            ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1, 64);
+            ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1, 100000);
             if (xt == 0) DBG(0, it, 1);
             uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
             const long long row_base = (long long)TC_OUT * (tile0 + it) - TC_LEAD;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         for (int it = 0; it < my_tiles; it++) {
             const int tile = tile0 + it;
             if (tid == 0) DBG(2, it, 0);
-            ptx::mbar_wait_sleep(&t_full[st], pht, 32);
+            ptx::mbar_wait_sleep(&t_full[st], pht, 100000);
             if (tid == 0) DBG(2, it, 1);
             ptx::tc_fence_after();
             /* ---- drain: 16 columns + the one before them, every limb accumulator; recombine modulo 2^32 ---- */
@@ -327,20 +327,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                     derotate(rq14(l_re), rq14(l_im), r_re, r_im, p_re, p_im);
                     rot_step(r_re, r_im, i_re, i_im);
                 }
-                uint32_t out[4];
-                int l_re = 0, l_im = 0;
+                int pcm[8], l_re = 0, l_im = 0;
+                float av[8];
+                uint32_t exact_mask = 0;
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     const int q_re = hi ? other[u] : mine[u], q_im = hi ? mine[u] : other[u];
                     int y_re, y_im;
                     derotate(rq14(q_re), rq14(q_im), r_re, r_im, y_re, y_im);
                     rot_step(r_re, r_im, i_re, i_im);
-                    const uint32_t pcm = (uint32_t)fm_pcm_bf(y_re, y_im, p_re, p_im, atan_s, ap) & 0xffffu;
-                    if (u & 1) out[u >> 1] |= pcm << 16; else out[u >> 1] = pcm;
+                    bool ex;
+                    pcm[u] = pcm_from_phi_fast(fm_phi_bf(y_re, y_im, p_re, p_im, atan_s, ap), av[u], ex);
+                    exact_mask |= (ex ? 1u : 0u) << u;
                     if (KEEP_IQ) { if (u < nvalid) iq_c[kfirst + u] = pack16(y_re, y_im); }
                     p_re = y_re; p_im = y_im;
                     if (u == nvalid - 1) { l_re = y_re; l_im = y_im; }
                 }
+                if (exact_mask) {       /* about 1 output in 60000: redo it in FP64 */
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (exact_mask & (1u << u)) pcm[u] = pcm_from_phi_exact(av[u]);
+                }
+                uint32_t out[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) out[u] = ((uint32_t)pcm[2 * u] & 0xffffu) | ((uint32_t)pcm[2 * u + 1] << 16);
                 if (nvalid == 8) {
                     *reinterpret_cast<uint4 *>(pcm_c + kfirst) = make_uint4(out[0], out[1], out[2], out[3]);
                 } else {
@@ -397,7 +407,8 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
             if (abs(re) > maxabs) maxabs = abs(re);
             if (abs(im) > maxabs) maxabs = abs(im);
         }
-    pl.mode = (maxabs <= 254) ? TC_MODE_SUM : TC_MODE_RADIX;
+    const int sum_terms = (maxabs + 126) / 127;         /* int8 terms needed to write every entry as a sum */
+    pl.mode = (sum_terms <= 4) ? TC_MODE_SUM : TC_MODE_RADIX;
     pl.accs = (pl.mode == TC_MODE_SUM) ? 2 : 3;
     pl.nt_stages = 512 / (pl.accs * TC_ACC_STRIDE);
 
@@ -409,15 +420,15 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
         const int n = (2 * taps + 31) / 32;
         for (int kk = 0; kk < n; kk++) qk.push_back({ q, kk });
     }
-    /* SUM mode: which chunks hold a non-zero second term anywhere in the bank */
-    std::vector<char> need2(qk.size(), 0);
+    /* SUM mode: the largest |entry| of every chunk anywhere in the bank decides how many terms it needs */
+    std::vector<int> chunk_max(qk.size(), 0);
     if (pl.mode == TC_MODE_SUM) {
         for (size_t n = 0; n < qk.size(); n++)
-            for (int c = 0; c < C && !need2[n]; c++)
-                for (int im = 0; im < 2 && !need2[n]; im++)
+            for (int c = 0; c < C; c++)
+                for (int im = 0; im < 2; im++)
                     for (int b = 0; b < 32; b++) {
-                        const int v = tap_entry(c_re, c_im, T, D, c, im, qk[n].q, qk[n].kk * 32 + b);
-                        if (v > 127 || v < -127) { need2[n] = 1; break; }
+                        const int v = abs(tap_entry(c_re, c_im, T, D, c, im, qk[n].q, qk[n].kk * 32 + b));
+                        if (v > chunk_max[n]) chunk_max[n] = v;
                     }
     }
     const uint32_t slab16 = (uint32_t)pl.R, nslab = (uint32_t)pl.Kp / 16;
@@ -434,20 +445,16 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
         pl.prog.push_back(m);
     };
     if (pl.mode == TC_MODE_SUM) {
-        /* term 0 everywhere, term 1 where needed; acc 0 = weight 2^8 (x hi, signed), acc 1 = weight 1 (x lo, unsigned) */
-        for (size_t n = 0; n < qk.size(); n++) {
-            const int ci = (int)pl.chunks.size();
-            pl.chunks.push_back({ qk[n].q, qk[n].kk, 0 });
-            emit(ci, false, qk[n].q, qk[n].kk, 0, 0);
-            emit(ci, true, qk[n].q, qk[n].kk, 1, 1);
-        }
-        for (size_t n = 0; n < qk.size(); n++) {
-            if (!need2[n]) continue;
-            const int ci = (int)pl.chunks.size();
-            pl.chunks.push_back({ qk[n].q, qk[n].kk, 1 });
-            emit(ci, false, qk[n].q, qk[n].kk, 0, 0);
-            emit(ci, true, qk[n].q, qk[n].kk, 1, 1);
-        }
+        /* term 0 everywhere, further terms where an entry exceeds 127 * term; acc 0 = weight 2^8 (x hi, signed),
+         * acc 1 = weight 1 (x lo, unsigned) */
+        for (int term = 0; term < (sum_terms > 0 ? sum_terms : 1); term++)
+            for (size_t n = 0; n < qk.size(); n++) {
+                if (term > 0 && chunk_max[n] <= 127 * term) continue;
+                const int ci = (int)pl.chunks.size();
+                pl.chunks.push_back({ qk[n].q, qk[n].kk, term });
+                emit(ci, false, qk[n].q, qk[n].kk, 0, 0);
+                emit(ci, true, qk[n].q, qk[n].kk, 1, 1);
+            }
     } else {
         /* term 0 = low byte (unsigned), term 1 = high byte (signed); accs: 0 = 2^16, 1 = 2^8, 2 = 1 */
         for (size_t n = 0; n < qk.size(); n++) {
@@ -493,8 +500,12 @@ void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_
                         const int v = (c < pl.C) ? tap_entry(c_re, c_im, pl.T, pl.D, c, is_im, ck.q, ck.kk * 32 + j2 * 16 + b) : 0;
                         int piece;
                         if (pl.mode == TC_MODE_SUM) {
-                            const int v1 = v > 127 ? 127 : (v < -127 ? -127 : v);
-                            piece = ck.term == 0 ? v1 : v - v1;
+                            int rest = v;
+                            piece = 0;
+                            for (int k = 0; k <= ck.term; k++) {
+                                piece = rest > 127 ? 127 : (rest < -127 ? -127 : rest);
+                                rest -= piece;
+                            }
                         } else {
                             piece = ck.term == 0 ? (v & 0xff) : ((v >> 8) & 0xff);
                         }
