@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         int s = 0, ph = 0;
         for (int it = 0; it < my_tiles; it++) {
             if (xt == 0) { DBG(0, it, 0); prefetch_tile(tile0 + it + 3); }
-            ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1, 100000);
+            ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, 256);
             if (xt == 0) DBG(0, it, 1);
             uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
             const long long row_base = (long long)TC_OUT * (tile0 + it) - TC_LEAD;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         for (int it = 0; it < my_tiles; it++) {
             const int tile = tile0 + it;
             if (tid == 0) DBG(2, it, 0);
-            ptx::mbar_wait_sleep(&t_full[st], pht, 100000);
+            ptx::mbar_wait_backoff(&t_full[st], pht, 64);
             if (tid == 0) DBG(2, it, 1);
             ptx::tc_fence_after();
             /* ---- drain: 16 columns + the one before them, every limb accumulator; recombine modulo 2^32 ---- */

@@ -67,6 +67,12 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, 
     }
 }
 
+/* for roles that run ahead of the pipeline: poll rarely, leave the issue slots to the warps doing arithmetic */
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 /* ---- 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier ---- */
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
