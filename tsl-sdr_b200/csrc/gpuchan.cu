@@ -234,6 +234,14 @@ __global__ void rot_prepass_table_kernel(int *__restrict__ rot_state, int nr_cha
     if (blockIdx.y == 0) rot_state[c] = tab[(k0 + K - m) % lam];
 }
 
+/* rot_state[c] = phase at output index k, for banks whose checkpoints come straight from the table */
+__global__ void rot_state_table_kernel(int *__restrict__ rot_state, int nr_channels, const uint32_t *__restrict__ mu,
+                                       const uint32_t *__restrict__ lambda, const int *__restrict__ cyc, unsigned long long k)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nr_channels) rot_state[c] = cyc[(size_t)c * ROT_LMAX + (k - mu[c]) % lambda[c]];
+}
+
 /* -------------------------------------------------------------------------------------- */
 struct FirFmParams {
     InWindow in;
@@ -743,17 +751,24 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
         cg.mode = 0; cg.KP = FIR_WARPS * h->R - 1; cg.sub = 1; cg.step = 16;
         nr_tiles = (int)((K + cg.KP - 1) / cg.KP);
     }
+    /* Tensor-core engine in steady state (every channel past its transient, cycle tabulated): the kernel reads the
+     * phases from the cycle table itself -- no prepass, no checkpoint traffic. */
+    const bool steady = h->all_cyclic && h->k_total >= h->mu_max + 1;
+    const bool tc_table = use_tc && steady;
     if (K > 0) {
         if ((size_t)nr_tiles > h->ckpt_tiles || K > h->pitch) return set_err(GPUCHAN_E_INVAL, "internal capacity exceeded");
-        if (h->all_cyclic && h->k_total >= h->mu_max + 1) {
+        if (tc_table) {
+            /* nothing to do */
+        } else if (steady) {
             dim3 g((h->C + 63) / 64, (nr_tiles + 15) / 16);
             rot_prepass_table_kernel<<<g, 64, 0, pre>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, cg,
                                                         nr_tiles, ckpt);
+            h->launches++;
         } else {
             rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, pre>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
                                                                  h->k_total, K, cg, nr_tiles, ckpt);
+            h->launches++;
         }
-        h->launches++;
         CUDA_TRY(cudaGetLastError());
     }
 
@@ -771,8 +786,9 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
         }
         return GPUCHAN_OK;
     };
+    const bool carry_in_kernel = use_tc && K > 0;
     if (use_tc) {
-        if (int rc = save_carry(pre)) return rc;
+        if (!carry_in_kernel) { if (int rc = save_carry(pre)) return rc; }
         if (pre != st) {
             CUDA_TRY(cudaEventRecord(h->ev_pre_done[pb], pre));
             CUDA_TRY(cudaStreamWaitEvent(st, h->ev_pre_done[pb], 0));
@@ -789,6 +805,11 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
             tb.tap_img = h->d_tap_img; tb.incr = h->d_incr; tb.ckpt = ckpt;
             tb.last_in = h->d_last[h->pp_last]; tb.last_out = h->d_last[h->pp_last ^ 1];
             tb.atan_tab = h->d_atan; tb.pcm = h->d_pcm[slot]; tb.iq_out = h->d_iq[slot]; tb.pitch = (long long)h->pitch;
+            if (tc_table) {
+                tb.ckpt = nullptr; tb.mu = h->d_mu; tb.lambda = h->d_lambda; tb.cyc = h->d_cyc; tb.cyc_pitch = ROT_LMAX;
+                tb.k_base = h->k_total;
+            }
+            if (keep > 0) { tb.carry_out = h->d_carry[h->pp_carry ^ 1]; tb.carry_from = from; tb.carry_keep = (int)keep; }
             tb.K = K; tb.geom = tg; tb.atan = h->atan;
             tb.dbg = h->d_dbg;
             tb.dbg_flags = (h->d_dbg && getenv("GPUCHAN_DEBUG_SKIP")) ? atoi(getenv("GPUCHAN_DEBUG_SKIP")) : 0;
@@ -965,6 +986,11 @@ extern "C" int gpuchan_get_rot_state(gpuchan_t *h, uint32_t channel, int16_t rot
 {
     if (!h || channel >= (uint32_t)h->C) return set_err(GPUCHAN_E_BADARGS, "bad argument");
     if (int rc = gpuchan_sync(h)) return rc;
+    if (h->engine == GPUCHAN_ENGINE_TC && h->all_cyclic && h->k_total >= h->mu_max + 1) {
+        rot_state_table_kernel<<<(h->C + 63) / 64, 64, 0, h->stream>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
     int w = 0;
     uint32_t mu = 0, lam = 0;
     CUDA_TRY(cudaMemcpy(&w, h->d_rot + channel, sizeof(int), cudaMemcpyDeviceToHost));

@@ -56,6 +56,13 @@ struct TcKernelParams {
     int D;
     const uint8_t *tap_img;
     const int *incr, *ckpt, *last_in;
+    const uint32_t *mu, *lambda;
+    const int *cyc;
+    int cyc_pitch;
+    unsigned long long k_base;
+    int *carry_out;
+    long long carry_from;
+    int carry_keep;
     int *last_out;
     const float2 *atan_tab;
     short *pcm;
@@ -209,6 +216,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             if (xt == 0) DBG(0, it, 2);
             if (++s == NB) { s = 0; ph ^= 1; }
         }
+        /* keep the tail of the window the next submit still needs (fewer than T samples) */
+        if (blockIdx.x == 0 && p.carry_out)
+            for (int i = xt; i < p.carry_keep; i += XF_THREADS) p.carry_out[i] = in_sample(p.in, p.carry_from + i);
     } else if (warp_u == MMA_WARP) {
         /* ================= MMA issuer =================
          * The whole warp walks the (warp-uniform) loops so that descriptors live in uniform registers; only the
@@ -264,6 +274,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         int *const iq_c = KEEP_IQ ? p.iq_out + (size_t)c * p.pitch : nullptr;
         AtanParams ap = p.atan;
         ap.use_fma = FMA ? 1 : 0;
+        /* Steady state (every channel on its limit cycle): the phase of the output before my first one comes from the
+         * channel's cycle table; it advances by TC_OUT outputs per tile. */
+        const bool table_mode = p.ckpt == nullptr;
+        uint32_t lam = 1, tph = 0, tstep = 0;
+        const int *tab = nullptr;
+        if (table_mode && live) {
+            lam = __ldg(p.lambda + c);
+            const unsigned long long g0 = p.k_base + (unsigned long long)TC_OUT * tile0 + 8 * blk - 1 - __ldg(p.mu + c);
+            tph = (uint32_t)(g0 % lam);
+            tstep = (uint32_t)TC_OUT % lam;
+            tab = p.cyc + (size_t)c * p.cyc_pitch;
+        }
 
         int st = 0, pht = 0;
         for (int it = 0; it < my_tiles; it++) {
@@ -314,7 +336,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             const long long kfirst = (long long)TC_OUT * tile + 8 * blk;        /* output index of this thread's first column */
             const int nvalid = (p.K - kfirst > 8) ? 8 : (int)(p.K - kfirst);
             if (live && nvalid > 0 && !(p.dbg_flags & 1)) {
-                const int cwk = __ldg(p.ckpt + ((size_t)tile * TC_SUB + blk) * p.C + c);
+                int cwk;
+                if (table_mode) {
+                    uint32_t ix = tph;
+                    if (kfirst == 0) { ix++; if (ix == lam) ix = 0; }      /* phase of output 0 itself */
+                    cwk = __ldg(tab + ix);
+                } else {
+                    cwk = __ldg(p.ckpt + ((size_t)tile * TC_SUB + blk) * p.C + c);
+                }
                 int r_re = lo16(cwk), r_im = hi16(cwk);
                 int p_re, p_im;
                 if (kfirst == 0) {
@@ -361,6 +390,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                 /* the thread that produced the submit's last output hands y[K-1] to the next submit */
                 if (kfirst + nvalid == p.K) p.last_out[c] = pack16(l_re, l_im);
             }
+            tph += tstep;
+            if (tph >= lam) tph -= lam;
             if (tid == 0) DBG(2, it, 4);
         }
     }
@@ -549,6 +580,8 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     memset(&p, 0, sizeof(p));
     p.in = b.in; p.D = pl.D;
     p.tap_img = b.tap_img; p.incr = b.incr; p.ckpt = b.ckpt; p.last_in = b.last_in; p.last_out = b.last_out;
+    p.mu = b.mu; p.lambda = b.lambda; p.cyc = b.cyc; p.cyc_pitch = b.cyc_pitch; p.k_base = b.k_base;
+    p.carry_out = b.carry_out; p.carry_from = b.carry_from; p.carry_keep = b.carry_keep;
     p.atan_tab = b.atan_tab; p.pcm = b.pcm; p.iq_out = b.iq_out; p.pitch = b.pitch; p.K = (long long)b.K;
     p.n_tiles = b.geom.n_tiles; p.total_tiles = b.geom.total_tiles;
     p.C = pl.C; p.G = pl.G; p.Kp = pl.Kp; p.Q = pl.Q; p.R = pl.R;

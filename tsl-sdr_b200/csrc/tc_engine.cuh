@@ -68,7 +68,14 @@ size_t tc_max_ckpt_tiles(const TcPlan &pl, long long max_K, int nr_sms);
 struct TcBatch {
     InWindow in;
     const uint8_t *tap_img;
-    const int *incr, *ckpt, *last_in;
+    const int *incr, *ckpt, *last_in;   /* ckpt == nullptr: derotator phases come straight from the cycle table */
+    const uint32_t *mu = nullptr, *lambda = nullptr;    /* per channel: transient length and period of the derotator */
+    const int *cyc = nullptr;           /* [C][cyc_pitch] one period of every channel's derotator sequence */
+    int cyc_pitch = 0;
+    unsigned long long k_base = 0;      /* stream index of this submit's output 0 */
+    int *carry_out = nullptr;           /* where to keep the input samples the next submit still needs ... */
+    long long carry_from = 0;           /* ... [carry_from, carry_from + carry_keep) of this submit's window */
+    int carry_keep = 0;
     int *last_out;
     const float2 *atan_tab;
     short *pcm;
