@@ -14,6 +14,10 @@
  *   filter/dc_blocker.h:72     dc_blocker_apply (-b)         GPUPAGER_F_DC_BLOCK (inside the decode kernel)
  *   pager/pager_pocsag.c:434   pager_pocsag_on_pcm           pocsag kernel (eye sync, slicer, BCH, message assembly)
  *   pager/pager_pocsag.h:8-22  on_numeric / on_alpha         gpupager_dispatch (same argument meaning, fired on the host)
+ *   decoder/decoder.c:689      pager_flex_new(...)           gpupager_create with decoder = GPUPAGER_DECODER_FLEX
+ *   pager/pager_flex.c:1401    pager_flex_on_pcm             flex kernel (Sync 1 / Sync 2 / block / BCH / vectors)
+ *   pager/pager_flex.h:16-83   on_alnum / on_num / on_siv    gpupager_dispatch_flex (same argument meaning)
+ *   decoder/decoder.c:621-626  -i (invert the input)         GPUPAGER_F_INVERT
  *
  * Stream contract: resampled sample m of a channel exists as soon as input samples up to n_m + M are
  * available (strict, polyphase_fir.c:184); the decoder consumes every resampled sample in order. Feeds
@@ -38,10 +42,17 @@ extern "C" {
 
 #define GPUPAGER_F_DC_BLOCK   0x1u   /* decoder -b (filter/dc_blocker.h), pole from cfg.dc_pole */
 #define GPUPAGER_F_KEEP_PCM   0x2u   /* keep the resampled PCM of the last feed (decoder -d tap) */
-#define GPUPAGER_F_NO_RESAMPLE 0x4u  /* input is already at 38400 Hz: bypass the resampler */
+#define GPUPAGER_F_NO_RESAMPLE 0x4u  /* input is already at the decoder's rate (38400 / 16000 Hz): bypass the resampler */
+#define GPUPAGER_F_INVERT     0x8u   /* decoder -i: negate every input sample (int16 wrap) before the resampler */
 
-#define GPUPAGER_MSG_NUMERIC  0
-#define GPUPAGER_MSG_ALPHA    1
+#define GPUPAGER_DECODER_POCSAG 0    /* decoder -m POCSAG (default) */
+#define GPUPAGER_DECODER_FLEX   1    /* decoder -m FLEX */
+
+#define GPUPAGER_MSG_NUMERIC    0    /* POCSAG numeric */
+#define GPUPAGER_MSG_ALPHA      1    /* POCSAG alphanumeric */
+#define GPUPAGER_MSG_FLEX_ALNUM 2    /* FLEX alphanumeric: function = phase, aux = {cycle, frame, fragmented, maildrop, seq} */
+#define GPUPAGER_MSG_FLEX_NUM   3    /* FLEX numeric / tone-with-digits: function = phase, aux = {cycle, frame} */
+#define GPUPAGER_MSG_FLEX_SIV   4    /* FLEX short instruction vector: aux = {cycle, frame, siv type, siv data} */
 #define GPUPAGER_MSG_TEXT_MAX 512
 
 typedef struct gpupager gpupager_t;
@@ -57,15 +68,19 @@ typedef struct gpupager_cfg {
     uint32_t flags;
     double   dc_pole;             /* decoder -p (default 0.9999) */
     const int16_t *taps;          /* [nr_taps] Q.14 int16 taps, see gpupager_quantize_taps */
+    uint32_t decoder;             /* GPUPAGER_DECODER_* */
+    uint32_t reserved;
 } gpupager_cfg;
 
 typedef struct gpupager_msg {
     uint32_t channel;
     uint32_t kind;                /* GPUPAGER_MSG_* */
-    uint32_t baud;                /* 512 / 1200 / 2400 */
-    uint32_t capcode;             /* as the reference reports it (pager_pocsag.c:362) */
-    uint32_t function;
+    uint32_t baud;                /* POCSAG 512 / 1200 / 2400; FLEX 1600 / 3200 / 6400 */
+    uint32_t capcode;             /* as the reference reports it (pager_pocsag.c:362, pager_flex.c:555,567); low 32 bits */
+    uint32_t function;            /* POCSAG function bits; FLEX phase (0 = A .. 3 = D) */
     uint32_t len;                 /* bytes in text */
+    uint32_t capcode_hi;          /* FLEX capcodes are uint64_t in the reference's callbacks */
+    uint32_t aux[6];              /* see GPUPAGER_MSG_FLEX_* */
     char     text[GPUPAGER_MSG_TEXT_MAX];
 } gpupager_msg;
 
@@ -74,6 +89,15 @@ typedef int (*gpupager_on_msg_func_t)(void *user, uint32_t channel, uint16_t bau
                                       const char *data, size_t data_len, uint8_t function);
 
 /* decoder/decoder.c:530-533: (int16_t)(coef * (1 << 14)) */
+/* Same argument meaning as pager/pager_flex.h:16-83, plus the channel index and a user pointer. */
+typedef int (*gpupager_on_flex_alnum_func_t)(void *user, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no,
+                                             uint8_t frame_no, uint64_t cap_code, int fragmented, int maildrop,
+                                             uint8_t seq_num, const char *message_bytes, size_t message_len);
+typedef int (*gpupager_on_flex_num_func_t)(void *user, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no,
+                                           uint8_t frame_no, uint64_t cap_code, const char *message_bytes, size_t message_len);
+typedef int (*gpupager_on_flex_siv_func_t)(void *user, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no,
+                                           uint8_t frame_no, uint64_t cap_code, uint8_t siv_msg_type, uint32_t data);
+
 int gpupager_quantize_taps(const double *coeffs, size_t nr, int16_t *taps_q14);
 
 int gpupager_create(gpupager_t **ph, const gpupager_cfg *cfg);
@@ -89,6 +113,9 @@ int gpupager_feed(gpupager_t *h, const int16_t *pcm_host, size_t pitch_samples, 
  * channel in decode order.  Either callback may be NULL.  Returns the number of messages in *nr_msgs. */
 int gpupager_dispatch(gpupager_t *h, gpupager_on_msg_func_t on_numeric, gpupager_on_msg_func_t on_alpha, void *user,
                       size_t *nr_msgs);
+/* FLEX banks: the three callbacks of pager/pager_flex.h.  Any of them may be NULL. */
+int gpupager_dispatch_flex(gpupager_t *h, gpupager_on_flex_alnum_func_t on_alnum, gpupager_on_flex_num_func_t on_num,
+                           gpupager_on_flex_siv_func_t on_siv, void *user, size_t *nr_msgs);
 /* Same, copying the records instead (at most cap; the rest stay queued). */
 int gpupager_poll(gpupager_t *h, gpupager_msg *out, size_t cap, size_t *nr_msgs);
 

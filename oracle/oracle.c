@@ -526,3 +526,486 @@ void orc_pocsag_on_pcm(orc_pocsag *p, const int16_t *pcm, size_t n)     /* pager
         }
     }
 }
+
+/* ---------------------------------------------------------------------- */
+/* a8  FLEX: pager/pager_flex.c (whole file); state pager/pager_flex_priv.h */
+/* ---------------------------------------------------------------------- */
+enum { FX_SYNC_1 = 0, FX_SYNC_2 = 1, FX_BLOCK = 2 };                                    /* pager_flex_priv.h:11-31 */
+enum { FS_SEARCH_BS1 = 0, FS_BS1, FS_A, FS_B, FS_INV_A, FS_FIW, FS_SYNCED };            /* :33-70 */
+enum { F2_COMMA = 0, F2_C, F2_INV_COMMA, F2_INV_C, F2_SYNCED };                         /* :113-138 */
+
+struct flex_coding { uint16_t seq_a, baud; uint8_t fsk_levels, sample_skip, sync_2_samples, sym_bits, sample_fudge;
+                     uint16_t symbols_per_block; uint8_t nr_phases; };
+static const struct flex_coding flex_codings[4] = {                                     /* pager_flex.c:47-96 */
+    { 0x78f3, 1600, 2, 9,  4, 1, 0, 2816, 1 },
+    { 0x84e7, 3200, 2, 4, 24, 1, 2, 5632, 2 },
+    { 0x4f97, 3200, 4, 9, 12, 2, 0, 2816, 2 },
+    { 0x215f, 6400, 4, 4, 32, 2, 2, 5632, 4 },
+};
+
+/* struct pager_flex_block laid out as the reference has it in memory (pager_flex_priv.h:175-233), as 32-bit
+ * words: 4 phases x (88 words + one word holding cur_bit | cur_word << 8 | base_word << 16), then nr_symbols,
+ * then phase_ff.  The reference indexes phase_words[] with unchecked offsets taken from the air (vector start
+ * words up to 127 + length 127, pager_flex.c:977,1003), so reads and in-place BCH fix-ups can land in a later
+ * phase or in these bookkeeping words; modelling the block as one flat array reproduces that.  Offsets past the
+ * block (the reference would read its own heap) abort the vector instead. */
+#define FX_PHASE_STRIDE 89
+#define FX_BLOCK_WORDS (4 * FX_PHASE_STRIDE + 2)
+
+struct orc_flex {
+    int16_t sample_range, sample_delta;
+    int state;
+    int16_t skip, skip_count;
+    uint8_t cycle_id, frame_id;
+    /* sync 1 */
+    uint32_t sync_words[10];
+    int sync_state;
+    uint8_t sample_counter, bit_counter;
+    uint32_t a; uint16_t b; uint32_t inv_a; uint32_t fiw;
+    int coding;                         /* -1 = none */
+    int32_t sum_high, sum_low;
+    unsigned cnt_high, cnt_low;
+    /* sync 2 */
+    int s2_state;
+    uint16_t nr_dots, c, inv_c;
+    uint8_t nr_c;
+    /* block */
+    uint32_t blk[FX_BLOCK_WORDS];
+    uint8_t cur_bit[4], cur_word[4], base_word[4];
+    int32_t nr_symbols;
+    int phase_ff;
+    char msg_buf[256];
+    size_t msg_len;
+    /* sink */
+    orc_msg *msgs;
+    size_t cap, n;
+};
+
+static uint8_t fx_cksum(uint32_t w)                                 /* pager_flex.c:107-119 */
+{
+    uint8_t s = 0;
+    w &= 0x1fffff;
+    for (int i = 0; i < 6; i++) { s += w & 0xf; w >>= 4; }
+    return s & 0xf;
+}
+
+static int fx_slice2(int16_t sample) { return !((uint16_t)sample >> 15); }             /* :129-138 */
+static int fx_slice4(const orc_flex *f, int16_t sample)                                 /* :148-171 */
+{
+    sample = (int16_t)(sample - f->sample_delta);
+    if (sample < 0) return (-sample > f->sample_range / 4) ? 0 : 1;
+    return (sample > f->sample_range / 4) ? 2 : 3;
+}
+static int fx_slice(const orc_flex *f, int16_t sample)
+{
+    return flex_codings[f->coding].fsk_levels == 2 ? fx_slice2(sample) : fx_slice4(f, sample);
+}
+
+static void fx_sync_reset(orc_flex *f)                              /* :209-233 */
+{
+    memset(f->sync_words, 0, sizeof(f->sync_words));
+    f->sync_state = FS_BS1;
+    f->sample_counter = 0; f->bit_counter = 0;
+    f->a = 0; f->b = 0; f->inv_a = 0; f->fiw = 0; f->coding = -1;
+    f->sum_high = f->sum_low = 0; f->cnt_high = f->cnt_low = 0;
+}
+
+static void fx_reset(orc_flex *f)                                   /* :238-262, :173-207 */
+{
+    f->state = FX_SYNC_1;
+    f->skip = 0; f->skip_count = 0;
+    f->sample_range = 0; f->sample_delta = 0;
+    f->frame_id = 0; f->cycle_id = 0;
+    fx_sync_reset(f);
+    f->s2_state = F2_COMMA; f->nr_dots = 0; f->c = 0; f->inv_c = 0; f->nr_c = 0;
+    f->nr_symbols = 0; f->phase_ff = 0;
+    for (int i = 0; i < 4; i++) { f->cur_bit[i] = 0; f->cur_word[i] = 0; f->base_word[i] = 0; }
+}
+
+orc_flex *orc_flex_new(size_t max_msgs)
+{
+    orc_flex *f = calloc(1, sizeof(*f));
+    f->msgs = calloc(max_msgs ? max_msgs : 1, sizeof(orc_msg));
+    f->cap = max_msgs;
+    fx_reset(f);
+    return f;
+}
+void orc_flex_delete(orc_flex *f) { if (f) { free(f->msgs); free(f); } }
+size_t orc_flex_msgs(orc_flex *f, orc_msg **msgs) { *msgs = f->msgs; return f->n; }
+
+static orc_msg *fx_msg(orc_flex *f, uint32_t kind, uint8_t phase, uint64_t capcode)
+{
+    if (f->n >= f->cap) return NULL;
+    orc_msg *m = &f->msgs[f->n++];
+    memset(m, 0, sizeof(*m));
+    m->kind = kind; m->baud = flex_codings[f->coding].baud; m->function = phase;
+    m->capcode_lo = (uint32_t)capcode; m->capcode_hi = (uint32_t)(capcode >> 32);
+    m->aux[0] = f->cycle_id; m->aux[1] = f->frame_id;
+    return m;
+}
+
+static void fx_range(orc_flex *f, int16_t sample)                   /* :352-358 and twins */
+{
+    if (sample > 0) { f->sum_high += sample; f->cnt_high++; }
+    else            { f->sum_low += sample;  f->cnt_low++; }
+}
+
+static void fx_sync_update(orc_flex *f, int16_t sample)             /* :295-458 */
+{
+    f->sample_counter = (uint8_t)((f->sample_counter + 1) % 10);
+    const uint32_t sym = (uint32_t)fx_slice2(sample);
+    uint32_t *w = &f->sync_words[f->sample_counter];
+    switch (f->sync_state) {
+    case FS_SEARCH_BS1:
+        *w = (*w << 1) | sym;
+        if (*w == 0xaaaaaaaau) { f->bit_counter = 1; f->sync_state = FS_BS1; }
+        break;
+    case FS_BS1:
+        *w = (*w << 1) | sym;
+        if (*w == 0xaaaaaaaau) {
+            f->bit_counter++;
+        } else {
+            if (f->bit_counter < 3) f->sync_state = FS_SEARCH_BS1;
+            else { f->sync_state = FS_A; f->sample_counter = f->bit_counter / 2; }
+            f->bit_counter = 0;
+        }
+        break;
+    case FS_A:
+        if (f->sample_counter == 0) {
+            f->a = (f->a << 1) | sym;
+            fx_range(f, sample);
+            if (++f->bit_counter == 32) { f->sync_state = FS_B; f->bit_counter = 0; }
+        }
+        break;
+    case FS_B:
+        if (f->sample_counter == 0) {
+            f->b = (uint16_t)((f->b << 1) | sym);
+            fx_range(f, sample);
+            if (++f->bit_counter == 16) { f->sync_state = FS_INV_A; f->bit_counter = 0; }
+        }
+        break;
+    case FS_INV_A:
+        if (f->sample_counter == 0) {
+            f->inv_a = (f->inv_a << 1) | sym;
+            fx_range(f, sample);
+            if (++f->bit_counter == 32) {
+                /* _pager_flex_sync_check_baud :264-287.  The second test, popcount(~seq_a ^ inv_a>>16) < 4, is
+                 * evaluated in int: ~seq_a has its upper 16 bits set, the count is always >= 16 -- dead. */
+                const uint16_t coding_a = (f->a >> 16) & 0xffff, inv_coding_a = (f->inv_a >> 16) & 0xffff;
+                int found = -1;
+                for (int i = 0; i < 4 && found < 0; i++)
+                    if (__builtin_popcount(flex_codings[i].seq_a ^ coding_a) < 4 ||
+                        __builtin_popcount(~flex_codings[i].seq_a ^ inv_coding_a) < 4) found = i;
+                if (found >= 0) { f->coding = found; f->sync_state = FS_FIW; }
+                else fx_sync_reset(f);
+                f->bit_counter = 0;
+            }
+        }
+        break;
+    case FS_FIW:
+        if (f->sample_counter == 0) {
+            f->fiw = (f->fiw >> 1) | (sym << 31);
+            fx_range(f, sample);
+            if (++f->bit_counter == 32) {
+                /* :438-442.  A zero count divides by zero in the reference (SIGFPE); here the frame is dropped. */
+                if (f->cnt_high == 0 || f->cnt_low == 0) { fx_reset(f); break; }
+                const int16_t hi = (int16_t)(f->sum_high / (int)f->cnt_high), lo = (int16_t)(f->sum_low / (int)f->cnt_low);
+                f->sample_range = (int16_t)(hi - lo);
+                f->sample_delta = (int16_t)(hi - (int)f->sample_range / 2);
+                f->sync_state = FS_SYNCED;
+            }
+        }
+        break;
+    default:
+        break;
+    }
+}
+
+static int fx_handle_fiw(orc_flex *f)                               /* :1312-1345 */
+{
+    uint32_t fiw = f->fiw & 0x7fffffffu;
+    if (orc_bch_decode(&fiw)) return 0;
+    f->cycle_id = (fiw >> 4) & 0xf;
+    f->frame_id = (fiw >> 8) & 0x7f;
+    return fx_cksum(fiw) == 0xf;
+}
+
+static void fx_sync2_update(orc_flex *f, int16_t sample)            /* :460-525 */
+{
+    const struct flex_coding *cd = &flex_codings[f->coding];
+    switch (f->s2_state) {
+    case F2_COMMA:
+        if (cd->sync_2_samples == ++f->nr_dots) f->s2_state = F2_C;
+        break;
+    case F2_C:
+        f->c = (uint16_t)((f->c << cd->sym_bits) | fx_slice(f, sample));
+        f->nr_c += cd->sym_bits;
+        if (f->nr_c == 16) { f->s2_state = F2_INV_COMMA; f->nr_dots = 0; }
+        break;
+    case F2_INV_COMMA:
+        if (cd->sync_2_samples == ++f->nr_dots) { f->s2_state = F2_INV_C; f->nr_c = 0; }
+        break;
+    case F2_INV_C:
+        f->inv_c = (uint16_t)((f->inv_c << cd->sym_bits) | fx_slice(f, sample));
+        f->nr_c += cd->sym_bits;
+        if (f->nr_c == 16) f->s2_state = F2_SYNCED;
+        break;
+    default:
+        break;
+    }
+}
+
+/* --- phase processing over the flat block image --- */
+#define FX_OOB 0xffffffffu
+static int fx_in(size_t idx) { return idx < FX_BLOCK_WORDS; }
+
+static int fx_decode_address(orc_flex *f, size_t ai, uint64_t *capcode, size_t *nr_words)     /* :527-573 */
+{
+    *capcode = 0; *nr_words = 0;
+    if (!fx_in(ai)) return -1;
+    if (orc_bch_decode(&f->blk[ai])) return -1;
+    const uint32_t first = f->blk[ai] &= 0x1fffff;
+    if ((first > 0x8000 && first <= 0x1e0000) || (first > 0x1f0000 && first < 0x1f7fff)) {
+        *capcode = first - 32768;
+    } else {
+        if (!fx_in(ai + 1)) return -1;
+        if (orc_bch_decode(&f->blk[ai + 1])) return -1;
+        const uint32_t second = f->blk[ai + 1] &= 0x1fffff;
+        *nr_words = 1;
+        *capcode = (uint32_t)(0x1f9001u + (((0x1fffffu - second) * 32768u) + first - 1u));    /* 32-bit arithmetic */
+    }
+    return 0;
+}
+
+static int fx_alnum(orc_flex *f, uint8_t phase, uint64_t capcode, uint32_t long_word, size_t base, size_t nr_words)  /* :597-681 */
+{
+    size_t first_char_word = 1;
+    int skip_word = 0;
+    uint32_t status;
+    if (long_word != 0xffffffffu) { first_char_word = 0; status = long_word; }
+    else {
+        if (!fx_in(base)) return -1;
+        status = f->blk[base];
+        if (orc_bch_decode(&status)) return -1;
+    }
+    const int fragment = (status & (1u << 10)) != 0;
+    const uint8_t seq = (status >> 11) & 3;
+    int maildrop = 0;
+    if (seq == 3) { skip_word = 1; maildrop = (status & (1u << 20)) != 0; }
+    for (size_t i = first_char_word; i < nr_words; i++) {
+        if (!fx_in(base + i)) return -1;
+        uint32_t cw = f->blk[base + i];
+        if (orc_bch_decode(&cw)) return -1;
+        if (skip_word) cw >>= 7;
+        for (size_t j = (size_t)skip_word; j < 3; j++) {
+            const uint8_t ch = cw & 0x7f;
+            if (ch != 0x3) f->msg_buf[f->msg_len++] = (char)ch; else break;
+            if (f->msg_len == 255) break;
+            cw >>= 7;
+        }
+        skip_word = 0;
+        if (f->msg_len == 255) break;
+    }
+    orc_msg *m = fx_msg(f, 2, phase, capcode);
+    if (m) { m->aux[2] = (uint32_t)fragment; m->aux[3] = (uint32_t)maildrop; m->aux[4] = seq;
+             m->len = (uint32_t)f->msg_len; memcpy(m->data, f->msg_buf, f->msg_len); }
+    return 0;
+}
+
+static const char fx_num_lut[16] = { '0','1','2','3','4','5','6','7','8','9','X','U',' ','-',']','[' };  /* :686-704 */
+
+static int fx_numeric(orc_flex *f, uint8_t phase, uint64_t capcode, uint32_t long_word, size_t base, size_t nr_words)  /* :709-824 */
+{
+    uint32_t cur = 0, next = 0;
+    size_t nr_bits = nr_words * 21, cur_bits = 19, next_offs = 0, next_bits = 21;
+    if (long_word != 0xffffffffu) {
+        cur = (long_word & 0x1fffff) >> 2;
+        nr_bits += 19; cur_bits = 19; next_offs = 0;
+    } else {
+        if (!fx_in(base)) return -1;
+        cur = f->blk[base];
+        if (orc_bch_decode(&cur)) return -1;
+        cur &= 0x1fffff; cur >>= 2;
+        cur_bits = 19; nr_bits -= 2; next_offs = 1;
+    }
+    if (next_offs < nr_words) {
+        if (!fx_in(base + next_offs)) return -1;
+        next = f->blk[base + next_offs];
+        if (orc_bch_decode(&next)) return -1;
+        next_bits = 21; next &= 0x1fffff;
+    }
+    nr_bits &= ~(size_t)3;
+    do {
+        const size_t rem = cur_bits & ~(size_t)3;
+        for (size_t i = 0; i < rem; i += 4) {
+            f->msg_buf[f->msg_len++] = fx_num_lut[cur & 0xf];
+            if (f->msg_len == 255) break;
+            cur >>= 4; cur_bits -= 4; nr_bits -= 4;
+        }
+        if (f->msg_len == 255) break;
+        if (cur_bits != 0 && nr_bits != 0) {
+            switch (cur_bits) {
+            case 1: cur |= (next & 0x7) << 1; next >>= 3; next_bits -= 3; break;
+            case 2: cur |= (next & 0x3) << 2; next >>= 2; next_bits -= 2; break;
+            case 3: cur |= (next & 0x1) << 3; next >>= 1; next_bits -= 1; break;
+            }
+            cur_bits = 4;
+        } else if (cur_bits == 0 && nr_bits != 0) {
+            cur = next; cur_bits = next_bits; next_bits = 21; next_offs++;
+            if (next_offs < nr_words) {
+                if (!fx_in(base + next_offs)) return -1;
+                next = f->blk[base + next_offs];
+                if (orc_bch_decode(&next)) return -1;
+                next &= 0x1fffff;
+            }
+        }
+    } while (nr_bits != 0);
+    orc_msg *m = fx_msg(f, 3, phase, capcode);
+    if (m) { m->len = (uint32_t)f->msg_len; memcpy(m->data, f->msg_buf, f->msg_len); }
+    return 0;
+}
+
+static int fx_tone(orc_flex *f, uint8_t phase, uint64_t capcode, uint32_t first, uint32_t second)   /* :829-883 */
+{
+    first &= 0x1fffff;
+    switch ((first >> 7) & 3) {
+    case 0: {
+        first >>= 9;
+        for (int i = 0; i < 3; i++) { f->msg_buf[f->msg_len++] = fx_num_lut[first & 0xf]; first >>= 4; }
+        if (second != 0xffffffffu) {
+            second &= 0x1fffff;
+            for (int i = 0; i < 5; i++) { f->msg_buf[f->msg_len++] = fx_num_lut[second & 0xf]; second >>= 4; }
+        }
+        orc_msg *m = fx_msg(f, 3, phase, capcode);
+        if (m) { m->len = (uint32_t)f->msg_len; memcpy(m->data, f->msg_buf, f->msg_len); }
+        return 0;
+    }
+    case 1: case 2: return 0;           /* logged only */
+    default: return -1;
+    }
+}
+
+static int fx_siv(orc_flex *f, uint8_t phase, uint64_t capcode, uint32_t vec)                      /* :885-933 */
+{
+    vec &= 0x7fffff;
+    if (fx_cksum(vec) != 0xf) return -1;
+    orc_msg *m = fx_msg(f, 4, phase, capcode);
+    if (m) { m->aux[2] = (vec >> 7) & 7; m->aux[3] = (vec >> 10) & 0x7ff; }
+    return 0;
+}
+
+static int fx_vector(orc_flex *f, uint8_t phase, uint64_t capcode, size_t vi, size_t nr_vec, size_t base)  /* :938-1033 */
+{
+    f->msg_len = 0;
+    for (size_t i = 0; i < nr_vec; i++) {
+        if (!fx_in(vi + i)) return -1;
+        if (orc_bch_decode(&f->blk[vi + i])) return -1;
+    }
+    const uint32_t vec = f->blk[vi];
+    if (fx_cksum(vec) != 0xf) return -1;
+    const uint8_t type = (vec >> 4) & 7;
+    const size_t start = (vec >> 7) & 0x7f;
+    const uint32_t long_word = (nr_vec == 2) ? f->blk[vi + 1] : 0xffffffffu;
+    size_t len;
+    switch (type) {
+    case 2: return fx_tone(f, phase, capcode, vec, long_word);
+    case 3:
+        len = ((vec >> 14) & 7) + 1;
+        if (nr_vec == 2) len -= 1;
+        return fx_numeric(f, phase, capcode, long_word, base + start, len);
+    case 5:
+        len = (vec >> 14) & 0x7f;
+        if (nr_vec == 2) len -= 1;      /* wraps to SIZE_MAX for length 0, like the reference */
+        return fx_alnum(f, phase, capcode, long_word, base + start, len);
+    case 1: return fx_siv(f, phase, capcode, vec);
+    default: return 0;                  /* unsupported types are logged only */
+    }
+}
+
+static void fx_phase_process(orc_flex *f, unsigned ph)                                              /* :1088-1198 */
+{
+    const size_t base = (size_t)ph * FX_PHASE_STRIDE;
+    uint32_t biw = f->blk[base] & 0x7fffffffu;
+    if (orc_bch_decode(&biw)) return;
+    if (fx_cksum(biw) != 0xf) return;
+    const uint8_t vsw = (biw >> 10) & 0x3f, eob = (biw >> 8) & 3;
+    if (eob > vsw) return;
+    /* extra BIWs (:1157-1159) only log */
+    const size_t addr_start = 1 + (size_t)eob;
+    for (size_t i = addr_start; i < vsw; i++) {
+        const size_t vec_offs = i + vsw - addr_start;
+        uint64_t capcode; size_t nr_words;
+        if (fx_decode_address(f, base + i, &capcode, &nr_words)) return;
+        (void)fx_vector(f, (uint8_t)ph, capcode, base + vec_offs, nr_words + 1, base);
+        i += nr_words;
+    }
+}
+
+static void fx_append_bit(orc_flex *f, int ph, int bit)                                             /* :1200-1222 */
+{
+    uint32_t *w = &f->blk[(size_t)ph * FX_PHASE_STRIDE + f->base_word[ph] + f->cur_word[ph]];
+    *w = (*w >> 1) | ((uint32_t)(bit != 0) << 31);
+    f->cur_word[ph] = (uint8_t)((f->cur_word[ph] + 1) % 8);
+    if (f->cur_word[ph] == 0) f->cur_bit[ph]++;
+    if (f->cur_bit[ph] == 32) { f->base_word[ph] += 8; f->cur_bit[ph] = 0; f->cur_word[ph] = 0; }
+}
+
+static void fx_block_update(orc_flex *f, int16_t sample)                                            /* :1224-1310 */
+{
+    const struct flex_coding *cd = &flex_codings[f->coding];
+    const int sym = fx_slice(f, sample);
+    switch (cd->nr_phases) {
+    case 1: fx_append_bit(f, 0, sym == 1); break;
+    case 2:
+        if (cd->fsk_levels == 2) { fx_append_bit(f, f->phase_ff ? 2 : 0, sym == 1); f->phase_ff = !f->phase_ff; }
+        else { fx_append_bit(f, 0, sym & 2); fx_append_bit(f, 2, sym & 1); }
+        break;
+    default:
+        if (!f->phase_ff) { fx_append_bit(f, 0, sym & 2); fx_append_bit(f, 1, sym & 1); }
+        else              { fx_append_bit(f, 2, sym & 2); fx_append_bit(f, 3, sym & 1); }
+        f->phase_ff = !f->phase_ff;
+        break;
+    }
+    if (++f->nr_symbols == cd->symbols_per_block) {
+        /* materialise the bookkeeping words of struct pager_flex_block before the unchecked walks */
+        for (int p = 0; p < 4; p++)
+            f->blk[(size_t)p * FX_PHASE_STRIDE + 88] = f->cur_bit[p] | (uint32_t)f->cur_word[p] << 8 | (uint32_t)f->base_word[p] << 16;
+        f->blk[4 * FX_PHASE_STRIDE] = (uint32_t)f->nr_symbols;
+        f->blk[4 * FX_PHASE_STRIDE + 1] = (uint32_t)f->phase_ff;
+        switch (cd->nr_phases) {
+        case 1: fx_phase_process(f, 0); break;
+        case 2: fx_phase_process(f, 0); fx_phase_process(f, 2); break;
+        default: for (unsigned p = 0; p < 4; p++) fx_phase_process(f, p); break;
+        }
+        fx_reset(f);
+    }
+}
+
+void orc_flex_on_pcm(orc_flex *f, const int16_t *pcm, size_t n)                                     /* :1401-1455 */
+{
+    for (size_t i = 0; i < n; i++) {
+        if (f->skip_count != 0) { f->skip_count--; continue; }
+        f->skip_count = f->skip;
+        switch (f->state) {
+        case FX_SYNC_1:
+            fx_sync_update(f, pcm[i]);
+            if (f->sync_state == FS_SYNCED) {
+                if (fx_handle_fiw(f)) {
+                    f->state = FX_SYNC_2;
+                    f->skip = flex_codings[f->coding].sample_skip;
+                    f->skip_count = (int16_t)(f->skip + flex_codings[f->coding].sample_fudge);
+                } else {
+                    fx_reset(f);
+                }
+            }
+            break;
+        case FX_SYNC_2:
+            fx_sync2_update(f, pcm[i]);
+            if (f->s2_state == F2_SYNCED) f->state = FX_BLOCK;
+            break;
+        case FX_BLOCK:
+            fx_block_update(f, pcm[i]);
+            break;
+        }
+    }
+}

@@ -87,6 +87,12 @@ class Oracle:
         L.orc_pocsag_msgs.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Msg))]
         L.orc_msg_size.restype = C.c_size_t
         assert L.orc_msg_size() == C.sizeof(Msg)
+        L.orc_flex_new.restype = C.c_void_p
+        L.orc_flex_new.argtypes = [C.c_size_t]
+        L.orc_flex_delete.argtypes = [C.c_void_p]
+        L.orc_flex_on_pcm.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_flex_msgs.restype = C.c_size_t
+        L.orc_flex_msgs.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Msg))]
 
     # a1
     def prepare_taps(self, lpf, offset_hz, fs, gain=1.0):
@@ -166,6 +172,22 @@ class Oracle:
         cnt = self.L.orc_pocsag_msgs(h, C.byref(pm))
         msgs = [pm[i].as_tuple() for i in range(cnt)]
         self.L.orc_pocsag_delete(h)
+        return msgs
+
+
+    # a8
+    def flex(self, pcm, chunk=0, max_msgs=4096):
+        pcm = _as_i16(pcm)
+        h = self.L.orc_flex_new(max_msgs)
+        n = len(pcm)
+        chunk = chunk or n
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            self.L.orc_flex_on_pcm(h, pcm[s:e].ctypes.data, e - s)
+        pm = C.POINTER(Msg)()
+        cnt = self.L.orc_flex_msgs(h, C.byref(pm))
+        msgs = [pm[i].as_tuple() for i in range(cnt)]
+        self.L.orc_flex_delete(h)
         return msgs
 
 

@@ -119,6 +119,20 @@ def main():
         out[f"ch{c}_meta"] = meta
         out[f"ch{c}_text"] = text
     np.savez_compressed(os.path.join(HERE, "pocsag_chain.npz"), **out)
+    # ---- 6. FLEX: all four codings, clean / corrupted / noisy frames straight into pager_flex_on_pcm ----
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import flexcases
+    out = {}
+    total = 0
+    for coding, trial, pcm in flexcases.all_cases():
+        m = ref.flex(pcm)
+        assert m == ref.flex(pcm, chunk=1000)
+        key = f"{coding.replace('/', '_')}_t{trial}"
+        out[key + "_crc"] = np.array([int(np.bitwise_xor.reduce(pcm.astype(np.int64) * np.arange(1, len(pcm) + 1))), len(pcm)])
+        out[key + "_meta"], out[key + "_text"] = flexcases.msgs_to_arrays(m)
+        total += len(m)
+    assert total > 300
+    np.savez_compressed(os.path.join(HERE, "flex.npz"), **out)
     print("golden fixtures written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

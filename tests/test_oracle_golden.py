@@ -100,3 +100,22 @@ def test_pocsag_chain_golden(oracle):
     # the quirk SURVEY.md a7 documents: address/function are reported bit-reversed, text keeps EOT + padding
     m = oracle.pocsag(z["ch0_res"])[0]
     assert (m[1], m[2], m[3], m[4], m[6]) == (1200, 93007, 3, 20, b"HELLO B200 TEST 42\x04\x00")
+
+
+def test_flex_golden(oracle):
+    """a8 pinned without the reference tree: tuples recorded from the reference's pager_flex objects."""
+    import flexcases
+    z = load("flex.npz")
+    total = 0
+    for coding, trial, pcm in flexcases.all_cases():
+        key = f"{coding.replace('/', '_')}_t{trial}"
+        crc, n = (int(v) for v in z[key + "_crc"])
+        assert len(pcm) == n and int(np.bitwise_xor.reduce(pcm.astype(np.int64) * np.arange(1, n + 1))) == crc
+        exp = flexcases.arrays_to_msgs(z[key + "_meta"], z[key + "_text"])
+        assert oracle.flex(pcm) == exp, key
+        assert oracle.flex(pcm, chunk=1000) == exp, key
+        total += len(exp)
+    assert total > 300
+    # the Appendix D template: short address 1234567, first fragment, sequence 3
+    m = flexcases.arrays_to_msgs(z["1600_2_t0_meta"], z["1600_2_t0_text"])
+    assert (2, 1600, 1234567, 0, 18, (3, 17, 0, 0, 3, 0), b"HELLO FLEX ON B200") in m

@@ -131,3 +131,31 @@ def test_dc_blocker(oracle, ref):
         exp = ref.resample(taps, 4, 5, pcm, use_dc=True, pole=pole)
         got = oracle.dc_block(oracle.resample(taps, 4, 5, pcm)[0][:len(exp)], pole)
         assert len(exp) > 1000 and np.array_equal(got, exp)
+
+
+def test_flex_decoder(oracle, ref):
+    """a8: every coding, clean / bit-flipped / noisy frames, whole-buffer and chunked: identical callback tuples."""
+    import flexcases
+    total = 0
+    for coding, trial, pcm in flexcases.all_cases():
+        exp = ref.flex(pcm)
+        assert oracle.flex(pcm) == exp, (coding, trial)
+        assert oracle.flex(pcm, chunk=777) == exp, (coding, trial)
+        total += len(exp)
+        if trial == 0:
+            kinds = {m[0] for m in exp}
+            assert kinds == {2, 3, 4} and all(m[1] == int(coding.split("/")[0]) for m in exp)
+    assert total > 300
+
+
+def test_random_pcm_into_flex(oracle, ref):
+    """Noise and stray sync patterns: false bit-syncs, unknown A words, uncorrectable FIWs."""
+    from tsl_sdr_b200 import flexsynth
+    for seed in range(6):
+        rng = np.random.default_rng(seed)
+        pcm = np.clip(np.round(rng.normal(0, 4000, 300000)), -32768, 32767).astype(np.int16)
+        lv = flexsynth.frame_levels("1600/2", 1, 2, {})[:10 * (40 + 32 + 32 + 16 + 32 + 20)]      # sync 1 with a truncated FIW
+        burst = np.round(lv * 5000).astype(np.int16)
+        for pos in range(3000, 280000, 50000):
+            pcm[pos:pos + len(burst)] = burst
+        assert oracle.flex(pcm) == ref.flex(pcm)

@@ -63,6 +63,7 @@ def _declare(L: C.CDLL) -> None:
     L.gpupager_feed.argtypes = [vp, vp, sz, sz]
     L.gpupager_dispatch.argtypes = [vp, ON_MSG, ON_MSG, vp, C.POINTER(sz)]
     L.gpupager_poll.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.gpupager_dispatch_flex.argtypes = [vp, ON_FLEX_ALNUM, ON_FLEX_NUM, ON_FLEX_SIV, vp, C.POINTER(sz)]
     L.gpupager_collect_pcm.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.gpupager_kernel_launches.restype = C.c_uint64
     L.gpupager_kernel_launches.argtypes = [vp]
@@ -83,14 +84,21 @@ class GpuPagerCfg(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("nr_channels", C.c_uint32), ("device", C.c_int32),
                 ("interpolate", C.c_uint32), ("decimate", C.c_uint32), ("nr_taps", C.c_uint32),
                 ("max_feed_samples", C.c_uint32), ("flags", C.c_uint32), ("dc_pole", C.c_double),
-                ("taps", C.POINTER(C.c_int16))]
+                ("taps", C.POINTER(C.c_int16)), ("decoder", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class GpuPagerMsg(C.Structure):
     _fields_ = [("channel", C.c_uint32), ("kind", C.c_uint32), ("baud", C.c_uint32), ("capcode", C.c_uint32),
-                ("function", C.c_uint32), ("len", C.c_uint32), ("text", C.c_char * 512)]
+                ("function", C.c_uint32), ("len", C.c_uint32), ("capcode_hi", C.c_uint32), ("aux", C.c_uint32 * 6),
+                ("text", C.c_char * 512)]
 
 
+ON_FLEX_ALNUM = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint64, C.c_int,
+                            C.c_int, C.c_uint8, C.POINTER(C.c_char), C.c_size_t)
+ON_FLEX_NUM = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint64,
+                          C.POINTER(C.c_char), C.c_size_t)
+ON_FLEX_SIV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint64, C.c_uint8,
+                          C.c_uint32)
 ON_MSG = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint32, C.POINTER(C.c_char), C.c_size_t, C.c_uint8)
 
 
@@ -101,5 +109,5 @@ EXPORTS = ["gpuchan_prepare_taps", "gpuchan_derot_increment", "gpuchan_db_to_gai
            "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error", "gpuchan_timing_enable", "gpuchan_in_flight", "gpuchan_discard", "gpuchan_host_alloc", "gpuchan_host_free", "gpuchan_tc_selftest", "gpuchan_debug_stamps", "gpuchan_stream_wait",
            "gpuchan_timing_read",
            "gpupager_quantize_taps", "gpupager_create", "gpupager_destroy", "gpupager_feed_device", "gpupager_feed",
-           "gpupager_dispatch", "gpupager_poll", "gpupager_collect_pcm", "gpupager_kernel_launches",
+           "gpupager_dispatch", "gpupager_dispatch_flex", "gpupager_poll", "gpupager_collect_pcm", "gpupager_kernel_launches",
            "gpupager_dropped_msgs", "gpupager_last_error"]

@@ -10,6 +10,11 @@
  *                     blocker (filter/dc_blocker.h:72-92), 3-rate eye sync detector, slicer, 16-word batch,
  *                     BCH(31,21) correction, address/alpha/numeric assembly (pager/pager_pocsag.c:82-543,
  *                     pager/bch_code.c:307-398).  Messages are queued per channel for the host callbacks.
+ *   flex_kernel       one thread per channel over the resampled 16000 Hz stream: optional DC blocker, Sync 1
+ *                     (10-phase bit-sync search, A / B / inverted A, FIW), slicer training, Sync 2, 4 codings
+ *                     (1600/2, 3200/2, 3200/4, 6400/4), block de-interleave into up to 4 phases, BCH + checksum,
+ *                     BIW / address / vector walk, alphanumeric / numeric / tone / SIV assembly
+ *                     (pager/pager_flex.c, whole file).
  *   pcm_carry_kernel  keeps the <= M input samples per channel the next feed still needs.
  *
  * All arithmetic is integer/bitwise and reproduces the reference bit for bit, including its quirks:
@@ -101,13 +106,15 @@ struct InPcm {
     const short *fresh;         /* [C][fresh_pitch] */
     long long carry_pitch, fresh_pitch;
     long long carry_len, total; /* window = carry_len + fresh_len samples, starting at global index base */
+    int invert;                 /* decoder -i: fresh samples are negated (int16 wrap); carried ones already were */
 };
 
 __device__ __forceinline__ int pcm_at(const InPcm &w, int c, long long i)
 {
     if (i < 0 || i >= w.total) return 0;
-    return (i < w.carry_len) ? (int)w.carry[(size_t)c * w.carry_pitch + i]
-                             : (int)w.fresh[(size_t)c * w.fresh_pitch + (i - w.carry_len)];
+    if (i < w.carry_len) return (int)w.carry[(size_t)c * w.carry_pitch + i];
+    const int v = (int)w.fresh[(size_t)c * w.fresh_pitch + (i - w.carry_len)];
+    return w.invert ? (int)(short)(-v) : v;
 }
 
 __global__ void resample_kernel(InPcm in, unsigned long long base, const short *__restrict__ phase_filters, int M,
@@ -212,6 +219,8 @@ __device__ void deliver(PocsagState &p, char *alpha, char *numeric, const MsgSin
         gpupager_msg *m = sink.msgs + (size_t)c * sink.cap + slot;
         m->channel = c; m->kind = is_alpha ? GPUPAGER_MSG_ALPHA : GPUPAGER_MSG_NUMERIC;
         m->baud = p.baud; m->capcode = p.capcode; m->function = p.function;
+        m->capcode_hi = 0;
+        for (int i = 0; i < 6; i++) m->aux[i] = 0;
         const uint32_t len = is_alpha ? p.n_alpha : p.n_numeric;
         m->len = len;
         const char *src = is_alpha ? alpha : numeric;
@@ -371,6 +380,492 @@ __global__ void pocsag_kernel(PocsagState *__restrict__ states, char *__restrict
     for (int i = 0; i < 75 + 32 + 16; i++) g.eye_reg[i] = p.eye_reg[i];
 }
 
+
+/* ============================================================================================== */
+/* FLEX (pager/pager_flex.c).  State mirrors struct pager_flex (pager/pager_flex_priv.h:238-326).   */
+/* ============================================================================================== */
+enum { FX_SYNC_1 = 0, FX_SYNC_2 = 1, FX_BLOCK = 2 };
+enum { FS_SEARCH_BS1 = 0, FS_BS1, FS_A, FS_B, FS_INV_A, FS_FIW, FS_SYNCED };
+enum { F2_COMMA = 0, F2_C, F2_INV_COMMA, F2_INV_C, F2_SYNCED };
+
+/* pager_flex.c:47-96 */
+struct FlexCoding { unsigned short seq_a, baud; unsigned char fsk_levels, sample_skip, sync_2_samples, sym_bits, sample_fudge;
+                    unsigned short symbols_per_block; unsigned char nr_phases; };
+__constant__ FlexCoding c_flex_codings[4] = {
+    { 0x78f3, 1600, 2, 9,  4, 1, 0, 2816, 1 },
+    { 0x84e7, 3200, 2, 4, 24, 1, 2, 5632, 2 },
+    { 0x4f97, 3200, 4, 9, 12, 2, 0, 2816, 2 },
+    { 0x215f, 6400, 4, 4, 32, 2, 2, 5632, 4 },
+};
+__constant__ char c_flex_num_lut[16] = { '0','1','2','3','4','5','6','7','8','9','X','U',' ','-',']','[' };   /* :686-704 */
+
+/* struct pager_flex_block as the reference lays it out in memory, in 32-bit words: 4 phases x (88 words + one word
+ * of cur_bit | cur_word << 8 | base_word << 16), nr_symbols, phase_ff.  The reference walks phase_words[] with
+ * unchecked offsets read off the air (start word <= 127, length <= 127), so reads and in-place BCH fix-ups may land
+ * in a later phase or in the bookkeeping words; one flat array reproduces that.  Offsets past the block (the
+ * reference would read its heap) end the vector instead. */
+constexpr int FX_PHASE_STRIDE = 89;
+constexpr int FX_BLOCK_WORDS = 4 * FX_PHASE_STRIDE + 2;
+
+struct FlexState {
+    int sample_range, sample_delta;             /* int16 values */
+    int state, skip, skip_count;
+    uint32_t cycle_id, frame_id;
+    int sync_state;
+    uint32_t sample_counter, bit_counter;       /* uint8 in the reference */
+    uint32_t a, b, inv_a, fiw;
+    int coding;
+    int sum_high, sum_low;
+    uint32_t cnt_high, cnt_low;
+    int s2_state;
+    uint32_t nr_dots, c, inv_c, nr_c;
+    int nr_symbols, phase_ff;
+    uint32_t msg_len;
+    int dc_x, dc_y, dc_acc;
+    uint32_t sync_words[10];
+    uint8_t cur_bit[4], cur_word[4], base_word[4];
+    uint32_t blk[FX_BLOCK_WORDS];
+    char msg_buf[256];
+};
+
+__device__ __forceinline__ uint32_t fx_cksum(uint32_t w)                       /* :107-119 */
+{
+    uint32_t s = 0;
+    w &= 0x1fffff;
+    for (int i = 0; i < 6; i++) { s += w & 0xf; w >>= 4; }
+    return s & 0xf;
+}
+
+__device__ __forceinline__ int fx_slice(const FlexState &f, int sample)        /* :129-171 */
+{
+    if (c_flex_codings[f.coding].fsk_levels == 2) return sample >= 0 ? 1 : 0;
+    sample = (int)(short)(sample - f.sample_delta);
+    if (sample < 0) return (-sample > f.sample_range / 4) ? 0 : 1;
+    return (sample > f.sample_range / 4) ? 2 : 3;
+}
+
+__device__ void fx_sync_reset(FlexState &f)                                    /* :209-233 */
+{
+    for (int i = 0; i < 10; i++) f.sync_words[i] = 0;
+    f.sync_state = FS_BS1;
+    f.sample_counter = 0; f.bit_counter = 0;
+    f.a = 0; f.b = 0; f.inv_a = 0; f.fiw = 0; f.coding = -1;
+    f.sum_high = f.sum_low = 0; f.cnt_high = f.cnt_low = 0;
+}
+
+__device__ void fx_reset(FlexState &f)                                         /* :173-262 */
+{
+    f.state = FX_SYNC_1;
+    f.skip = 0; f.skip_count = 0;
+    f.sample_range = 0; f.sample_delta = 0;
+    f.frame_id = 0; f.cycle_id = 0;
+    fx_sync_reset(f);
+    f.s2_state = F2_COMMA; f.nr_dots = 0; f.c = 0; f.inv_c = 0; f.nr_c = 0;
+    f.nr_symbols = 0; f.phase_ff = 0;
+    for (int i = 0; i < 4; i++) { f.cur_bit[i] = 0; f.cur_word[i] = 0; f.base_word[i] = 0; }
+}
+
+__global__ void flex_init_kernel(FlexState *states, int nr_channels)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < nr_channels) fx_reset(states[c]);
+}
+
+__device__ gpupager_msg *fx_msg(const FlexState &f, const MsgSink &sink, int c, uint32_t kind, uint32_t phase, uint64_t capcode)
+{
+    const uint32_t slot = sink.count[c];
+    if (slot >= sink.cap) { atomicAdd(sink.dropped, 1ull); return nullptr; }
+    gpupager_msg *m = sink.msgs + (size_t)c * sink.cap + slot;
+    m->channel = c; m->kind = kind; m->baud = c_flex_codings[f.coding].baud;
+    m->capcode = (uint32_t)capcode; m->capcode_hi = (uint32_t)(capcode >> 32);
+    m->function = phase; m->len = 0;
+    m->aux[0] = f.cycle_id; m->aux[1] = f.frame_id; m->aux[2] = m->aux[3] = m->aux[4] = m->aux[5] = 0;
+    m->text[0] = 0;
+    sink.count[c] = slot + 1;
+    return m;
+}
+
+__device__ void fx_msg_text(gpupager_msg *m, const FlexState &f)
+{
+    if (!m) return;
+    m->len = f.msg_len;
+    for (uint32_t i = 0; i < f.msg_len; i++) m->text[i] = f.msg_buf[i];
+    m->text[f.msg_len] = 0;
+}
+
+__device__ __forceinline__ void fx_range(FlexState &f, int sample)             /* :352-358 and twins */
+{
+    if (sample > 0) { f.sum_high += sample; f.cnt_high++; }
+    else            { f.sum_low += sample;  f.cnt_low++; }
+}
+
+__device__ void fx_sync_update(FlexState &f, int sample)                       /* :295-458 */
+{
+    f.sample_counter = (f.sample_counter + 1) % 10;
+    const uint32_t sym = sample >= 0 ? 1u : 0u;
+    switch (f.sync_state) {
+    case FS_SEARCH_BS1: {
+        uint32_t &w = f.sync_words[f.sample_counter];
+        w = (w << 1) | sym;
+        if (w == 0xaaaaaaaau) { f.bit_counter = 1; f.sync_state = FS_BS1; }
+        break;
+    }
+    case FS_BS1: {
+        uint32_t &w = f.sync_words[f.sample_counter];
+        w = (w << 1) | sym;
+        if (w == 0xaaaaaaaau) {
+            f.bit_counter = (f.bit_counter + 1) & 0xff;
+        } else {
+            if (f.bit_counter < 3) f.sync_state = FS_SEARCH_BS1;
+            else { f.sync_state = FS_A; f.sample_counter = f.bit_counter / 2; }
+            f.bit_counter = 0;
+        }
+        break;
+    }
+    case FS_A:
+        if (f.sample_counter == 0) {
+            f.a = (f.a << 1) | sym;
+            fx_range(f, sample);
+            if (++f.bit_counter == 32) { f.sync_state = FS_B; f.bit_counter = 0; }
+        }
+        break;
+    case FS_B:
+        if (f.sample_counter == 0) {
+            f.b = ((f.b << 1) | sym) & 0xffffu;
+            fx_range(f, sample);
+            if (++f.bit_counter == 16) { f.sync_state = FS_INV_A; f.bit_counter = 0; }
+        }
+        break;
+    case FS_INV_A:
+        if (f.sample_counter == 0) {
+            f.inv_a = (f.inv_a << 1) | sym;
+            fx_range(f, sample);
+            if (++f.bit_counter == 32) {
+                /* _pager_flex_sync_check_baud (:264-287): only the A word decides -- the reference's test on the
+                 * inverted word is evaluated in int, where ~seq_a has 16 extra one bits, and can never pass. */
+                const uint32_t coding_a = (f.a >> 16) & 0xffffu;
+                int found = -1;
+                for (int i = 0; i < 4 && found < 0; i++)
+                    if (__popc((uint32_t)c_flex_codings[i].seq_a ^ coding_a) < 4) found = i;
+                if (found >= 0) { f.coding = found; f.sync_state = FS_FIW; }
+                else fx_sync_reset(f);
+                f.bit_counter = 0;
+            }
+        }
+        break;
+    case FS_FIW:
+        if (f.sample_counter == 0) {
+            f.fiw = (f.fiw >> 1) | (sym << 31);
+            fx_range(f, sample);
+            if (++f.bit_counter == 32) {
+                /* :438-442.  A zero count is a division by zero (SIGFPE) in the reference; the frame is dropped here. */
+                if (f.cnt_high == 0 || f.cnt_low == 0) { fx_reset(f); break; }
+                const int hi = (int)(short)(f.sum_high / (int)f.cnt_high), lo = (int)(short)(f.sum_low / (int)f.cnt_low);
+                f.sample_range = (int)(short)(hi - lo);
+                f.sample_delta = (int)(short)(hi - f.sample_range / 2);
+                f.sync_state = FS_SYNCED;
+            }
+        }
+        break;
+    default:
+        break;
+    }
+}
+
+__device__ void fx_sync2_update(FlexState &f, int sample)                      /* :460-525 */
+{
+    const FlexCoding &cd = c_flex_codings[f.coding];
+    switch (f.s2_state) {
+    case F2_COMMA:
+        f.nr_dots = (f.nr_dots + 1) & 0xffffu;
+        if (cd.sync_2_samples == f.nr_dots) f.s2_state = F2_C;
+        break;
+    case F2_C:
+        f.c = ((f.c << cd.sym_bits) | (uint32_t)fx_slice(f, sample)) & 0xffffu;
+        f.nr_c += cd.sym_bits;
+        if (f.nr_c == 16) { f.s2_state = F2_INV_COMMA; f.nr_dots = 0; }
+        break;
+    case F2_INV_COMMA:
+        f.nr_dots = (f.nr_dots + 1) & 0xffffu;
+        if (cd.sync_2_samples == f.nr_dots) { f.s2_state = F2_INV_C; f.nr_c = 0; }
+        break;
+    case F2_INV_C:
+        f.inv_c = ((f.inv_c << cd.sym_bits) | (uint32_t)fx_slice(f, sample)) & 0xffffu;
+        f.nr_c += cd.sym_bits;
+        if (f.nr_c == 16) f.s2_state = F2_SYNCED;
+        break;
+    default:
+        break;
+    }
+}
+
+__device__ __forceinline__ bool fx_in(size_t idx) { return idx < (size_t)FX_BLOCK_WORDS; }
+
+/* :597-681 */
+__device__ int fx_alnum(FlexState &f, const MsgSink &sink, int c, uint32_t phase, uint64_t capcode, uint32_t long_word,
+                        size_t base, size_t nr_words)
+{
+    size_t first_char_word = 1;
+    int skip_word = 0;
+    uint32_t status;
+    if (long_word != 0xffffffffu) { first_char_word = 0; status = long_word; }
+    else {
+        if (!fx_in(base)) return -1;
+        status = f.blk[base];
+        if (bch_decode(status)) return -1;
+    }
+    const uint32_t fragment = (status >> 10) & 1;
+    const uint32_t seq = (status >> 11) & 3;
+    uint32_t maildrop = 0;
+    if (seq == 3) { skip_word = 1; maildrop = (status >> 20) & 1; }
+    for (size_t i = first_char_word; i < nr_words; i++) {
+        if (!fx_in(base + i)) return -1;
+        uint32_t cw = f.blk[base + i];
+        if (bch_decode(cw)) return -1;
+        if (skip_word) cw >>= 7;
+        for (int j = skip_word; j < 3; j++) {
+            const uint32_t ch = cw & 0x7f;
+            if (ch != 0x3) f.msg_buf[f.msg_len++] = (char)ch; else break;
+            if (f.msg_len == 255) break;
+            cw >>= 7;
+        }
+        skip_word = 0;
+        if (f.msg_len == 255) break;
+    }
+    gpupager_msg *m = fx_msg(f, sink, c, GPUPAGER_MSG_FLEX_ALNUM, phase, capcode);
+    if (m) { m->aux[2] = fragment; m->aux[3] = maildrop; m->aux[4] = seq; }
+    fx_msg_text(m, f);
+    return 0;
+}
+
+/* :709-824 */
+__device__ int fx_numeric(FlexState &f, const MsgSink &sink, int c, uint32_t phase, uint64_t capcode, uint32_t long_word,
+                          size_t base, size_t nr_words)
+{
+    uint32_t cur = 0, next = 0;
+    unsigned long long nr_bits = (unsigned long long)nr_words * 21, cur_bits = 19, next_offs = 0, next_bits = 21;
+    if (long_word != 0xffffffffu) {
+        cur = (long_word & 0x1fffff) >> 2;
+        nr_bits += 19; cur_bits = 19; next_offs = 0;
+    } else {
+        if (!fx_in(base)) return -1;
+        cur = f.blk[base];
+        if (bch_decode(cur)) return -1;
+        cur &= 0x1fffff; cur >>= 2;
+        cur_bits = 19; nr_bits -= 2; next_offs = 1;
+    }
+    if (next_offs < nr_words) {
+        if (!fx_in(base + next_offs)) return -1;
+        next = f.blk[base + next_offs];
+        if (bch_decode(next)) return -1;
+        next_bits = 21; next &= 0x1fffff;
+    }
+    nr_bits &= ~3ull;
+    do {
+        const unsigned long long rem = cur_bits & ~3ull;
+        for (unsigned long long i = 0; i < rem; i += 4) {
+            f.msg_buf[f.msg_len++] = c_flex_num_lut[cur & 0xf];
+            if (f.msg_len == 255) break;
+            cur >>= 4; cur_bits -= 4; nr_bits -= 4;
+        }
+        if (f.msg_len == 255) break;
+        if (cur_bits != 0 && nr_bits != 0) {
+            switch (cur_bits) {
+            case 1: cur |= (next & 0x7) << 1; next >>= 3; next_bits -= 3; break;
+            case 2: cur |= (next & 0x3) << 2; next >>= 2; next_bits -= 2; break;
+            case 3: cur |= (next & 0x1) << 3; next >>= 1; next_bits -= 1; break;
+            }
+            cur_bits = 4;
+        } else if (cur_bits == 0 && nr_bits != 0) {
+            cur = next; cur_bits = next_bits; next_bits = 21; next_offs++;
+            if (next_offs < nr_words) {
+                if (!fx_in(base + next_offs)) return -1;
+                next = f.blk[base + next_offs];
+                if (bch_decode(next)) return -1;
+                next &= 0x1fffff;
+            }
+        }
+    } while (nr_bits != 0);
+    fx_msg_text(fx_msg(f, sink, c, GPUPAGER_MSG_FLEX_NUM, phase, capcode), f);
+    return 0;
+}
+
+/* :829-883 */
+__device__ int fx_tone(FlexState &f, const MsgSink &sink, int c, uint32_t phase, uint64_t capcode, uint32_t first, uint32_t second)
+{
+    first &= 0x1fffff;
+    switch ((first >> 7) & 3) {
+    case 0:
+        first >>= 9;
+        for (int i = 0; i < 3; i++) { f.msg_buf[f.msg_len++] = c_flex_num_lut[first & 0xf]; first >>= 4; }
+        if (second != 0xffffffffu) {
+            second &= 0x1fffff;
+            for (int i = 0; i < 5; i++) { f.msg_buf[f.msg_len++] = c_flex_num_lut[second & 0xf]; second >>= 4; }
+        }
+        fx_msg_text(fx_msg(f, sink, c, GPUPAGER_MSG_FLEX_NUM, phase, capcode), f);
+        return 0;
+    case 1: case 2: return 0;           /* the reference only logs these */
+    default: return -1;
+    }
+}
+
+/* :938-1033 */
+__device__ int fx_vector(FlexState &f, const MsgSink &sink, int c, uint32_t phase, uint64_t capcode, size_t vi, size_t nr_vec,
+                         size_t base)
+{
+    f.msg_len = 0;
+    for (size_t i = 0; i < nr_vec; i++) {
+        if (!fx_in(vi + i)) return -1;
+        if (bch_decode(f.blk[vi + i])) return -1;
+    }
+    const uint32_t vec = f.blk[vi];
+    if (fx_cksum(vec) != 0xf) return -1;
+    const uint32_t type = (vec >> 4) & 7;
+    const size_t start = (vec >> 7) & 0x7f;
+    const uint32_t long_word = (nr_vec == 2) ? f.blk[vi + 1] : 0xffffffffu;
+    size_t len;
+    switch (type) {
+    case 2: return fx_tone(f, sink, c, phase, capcode, vec, long_word);
+    case 3:
+        len = ((vec >> 14) & 7) + 1;
+        if (nr_vec == 2) len -= 1;
+        return fx_numeric(f, sink, c, phase, capcode, long_word, base + start, len);
+    case 5:
+        len = (vec >> 14) & 0x7f;
+        if (nr_vec == 2) len -= 1;      /* wraps for length 0, like the reference's size_t */
+        return fx_alnum(f, sink, c, phase, capcode, long_word, base + start, len);
+    case 1: {                           /* short instruction vector, :885-933 */
+        const uint32_t v = vec & 0x7fffff;
+        if (fx_cksum(v) != 0xf) return -1;
+        gpupager_msg *m = fx_msg(f, sink, c, GPUPAGER_MSG_FLEX_SIV, phase, capcode);
+        if (m) { m->aux[2] = (v >> 7) & 7; m->aux[3] = (v >> 10) & 0x7ff; }
+        return 0;
+    }
+    default: return 0;                  /* unsupported vector types are logged only */
+    }
+}
+
+/* :1088-1198 with _pager_flex_decode_address :527-573 */
+__device__ void fx_phase_process(FlexState &f, const MsgSink &sink, int c, uint32_t ph)
+{
+    const size_t base = (size_t)ph * FX_PHASE_STRIDE;
+    uint32_t biw = f.blk[base] & 0x7fffffffu;
+    if (bch_decode(biw)) return;
+    if (fx_cksum(biw) != 0xf) return;
+    const uint32_t vsw = (biw >> 10) & 0x3f, eob = (biw >> 8) & 3;
+    if (eob > vsw) return;
+    const size_t addr_start = 1 + (size_t)eob;
+    for (size_t i = addr_start; i < vsw; i++) {
+        const size_t vec_offs = i + vsw - addr_start;
+        const size_t ai = base + i;
+        if (!fx_in(ai)) return;
+        if (bch_decode(f.blk[ai])) return;
+        const uint32_t first = f.blk[ai] &= 0x1fffff;
+        uint64_t capcode;
+        size_t nr_words = 0;
+        if ((first > 0x8000 && first <= 0x1e0000) || (first > 0x1f0000 && first < 0x1f7fff)) {
+            capcode = first - 32768;
+        } else {
+            if (!fx_in(ai + 1)) return;
+            if (bch_decode(f.blk[ai + 1])) return;
+            const uint32_t second = f.blk[ai + 1] &= 0x1fffff;
+            nr_words = 1;
+            capcode = (uint32_t)(0x1f9001u + (((0x1fffffu - second) * 32768u) + first - 1u));     /* 32-bit arithmetic */
+        }
+        (void)fx_vector(f, sink, c, ph, capcode, base + vec_offs, nr_words + 1, base);
+        i += nr_words;
+    }
+}
+
+__device__ __forceinline__ void fx_append_bit(FlexState &f, int ph, bool bit)  /* :1200-1222 */
+{
+    uint32_t &w = f.blk[ph * FX_PHASE_STRIDE + f.base_word[ph] + f.cur_word[ph]];
+    w = (w >> 1) | ((uint32_t)bit << 31);
+    f.cur_word[ph] = (uint8_t)((f.cur_word[ph] + 1) % 8);
+    if (f.cur_word[ph] == 0) f.cur_bit[ph]++;
+    if (f.cur_bit[ph] == 32) { f.base_word[ph] += 8; f.cur_bit[ph] = 0; f.cur_word[ph] = 0; }
+}
+
+__device__ void fx_block_update(FlexState &f, const MsgSink &sink, int c, int sample)    /* :1224-1310 */
+{
+    const FlexCoding &cd = c_flex_codings[f.coding];
+    const int sym = fx_slice(f, sample);
+    switch (cd.nr_phases) {
+    case 1: fx_append_bit(f, 0, sym == 1); break;
+    case 2:
+        if (cd.fsk_levels == 2) { fx_append_bit(f, f.phase_ff ? 2 : 0, sym == 1); f.phase_ff = !f.phase_ff; }
+        else { fx_append_bit(f, 0, (sym & 2) != 0); fx_append_bit(f, 2, (sym & 1) != 0); }
+        break;
+    default:
+        if (!f.phase_ff) { fx_append_bit(f, 0, (sym & 2) != 0); fx_append_bit(f, 1, (sym & 1) != 0); }
+        else             { fx_append_bit(f, 2, (sym & 2) != 0); fx_append_bit(f, 3, (sym & 1) != 0); }
+        f.phase_ff = !f.phase_ff;
+        break;
+    }
+    if (++f.nr_symbols == cd.symbols_per_block) {
+        for (int p = 0; p < 4; p++)
+            f.blk[p * FX_PHASE_STRIDE + 88] = f.cur_bit[p] | (uint32_t)f.cur_word[p] << 8 | (uint32_t)f.base_word[p] << 16;
+        f.blk[4 * FX_PHASE_STRIDE] = (uint32_t)f.nr_symbols;
+        f.blk[4 * FX_PHASE_STRIDE + 1] = (uint32_t)f.phase_ff;
+        if (cd.nr_phases == 1) fx_phase_process(f, sink, c, 0);
+        else if (cd.nr_phases == 2) { fx_phase_process(f, sink, c, 0); fx_phase_process(f, sink, c, 2); }
+        else for (uint32_t p = 0; p < 4; p++) fx_phase_process(f, sink, c, p);
+        fx_reset(f);
+    }
+}
+
+/* pager_flex_on_pcm (:1401-1455), one thread per channel, state worked on in place (L1/L2 resident) */
+__global__ void flex_kernel(FlexState *__restrict__ states, int nr_channels, short *__restrict__ pcm, long long pitch, unsigned n,
+                            MsgSink sink, int use_dc, int dc_p)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nr_channels) return;
+    FlexState &f = states[c];
+    short *x = pcm + (size_t)c * pitch;
+    for (unsigned i = 0; i < n; i++) {
+        int sample = x[i];
+        if (use_dc) {                       /* filter/dc_blocker.h:79-88 */
+            f.dc_acc -= f.dc_x;
+            f.dc_x = sample << 14;
+            f.dc_acc += f.dc_x - dc_p * f.dc_y;
+            f.dc_y = f.dc_acc >> 14;
+            sample = (int)(short)f.dc_y;
+            x[i] = (short)sample;
+        }
+        if (f.skip_count != 0) { f.skip_count--; continue; }
+        f.skip_count = f.skip;
+        switch (f.state) {
+        case FX_SYNC_1:
+            fx_sync_update(f, sample);
+            if (f.sync_state == FS_SYNCED) {
+                /* _pager_flex_handle_fiw :1312-1345 */
+                uint32_t fiw = f.fiw & 0x7fffffffu;
+                bool ok = bch_decode(fiw) == 0;
+                if (ok) {
+                    f.cycle_id = (fiw >> 4) & 0xf;
+                    f.frame_id = (fiw >> 8) & 0x7f;
+                    ok = fx_cksum(fiw) == 0xf;
+                }
+                if (ok) {
+                    f.state = FX_SYNC_2;
+                    f.skip = c_flex_codings[f.coding].sample_skip;
+                    f.skip_count = f.skip + c_flex_codings[f.coding].sample_fudge;
+                } else {
+                    fx_reset(f);
+                }
+            }
+            break;
+        case FX_SYNC_2:
+            fx_sync2_update(f, sample);
+            if (f.s2_state == F2_SYNCED) f.state = FX_BLOCK;
+            break;
+        default:
+            fx_block_update(f, sink, c, sample);
+            break;
+        }
+    }
+}
+
 } // namespace
 
 /* ------------------------------------------------------------------------------------------ */
@@ -396,7 +891,9 @@ struct gpupager {
     short *d_res = nullptr;             /* resampled output of the last feed [C][res_pitch] */
     long long res_pitch = 0;
     size_t last_out = 0;
+    int decoder = GPUPAGER_DECODER_POCSAG;
     PocsagState *d_states = nullptr;
+    FlexState *d_fstates = nullptr;
     char *d_text = nullptr;
     uint32_t msg_cap = 32;
     gpupager_msg *d_msgs = nullptr;
@@ -411,7 +908,7 @@ static void pager_free(gpupager *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_phase); cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_stage); cudaFree(h->d_res);
-    cudaFree(h->d_states); cudaFree(h->d_text); cudaFree(h->d_msgs); cudaFree(h->d_count); cudaFree(h->d_dropped);
+    cudaFree(h->d_states); cudaFree(h->d_fstates); cudaFree(h->d_text); cudaFree(h->d_msgs); cudaFree(h->d_count); cudaFree(h->d_dropped);
     if (h->ev_own) cudaEventDestroy(h->ev_own);
     if (h->ev_ext) cudaEventDestroy(h->ev_ext);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -424,6 +921,8 @@ extern "C" int gpupager_create(gpupager_t **ph, const gpupager_cfg *cfg)
     *ph = nullptr;
     if (cfg->struct_size != sizeof(gpupager_cfg)) return perr(GPUPAGER_E_BADARGS, "gpupager_cfg size mismatch");
     const bool bypass = (cfg->flags & GPUPAGER_F_NO_RESAMPLE) != 0;
+    if (cfg->decoder != GPUPAGER_DECODER_POCSAG && cfg->decoder != GPUPAGER_DECODER_FLEX)
+        return perr(GPUPAGER_E_BADARGS, "unknown decoder %u", cfg->decoder);
     if (!cfg->nr_channels || !cfg->max_feed_samples) return perr(GPUPAGER_E_BADARGS, "incomplete configuration");
     if (!bypass && (!cfg->interpolate || !cfg->decimate || !cfg->nr_taps || !cfg->taps))
         return perr(GPUPAGER_E_BADARGS, "resampler needs interpolate, decimate and taps");
@@ -436,6 +935,7 @@ extern "C" int gpupager_create(gpupager_t **ph, const gpupager_cfg *cfg)
     gpupager *h = new (std::nothrow) gpupager();
     if (!h) return perr(GPUPAGER_E_NOMEM, "out of memory");
     h->device = cfg->device; h->C = (int)cfg->nr_channels; h->flags = cfg->flags; h->max_feed = cfg->max_feed_samples;
+    h->decoder = (int)cfg->decoder;
     if (cfg->flags & GPUPAGER_F_DC_BLOCK) {
         const double pole = cfg->dc_pole != 0.0 ? cfg->dc_pole : 0.9999;
         h->dc_p = (int16_t)((1.0 - pole) * (double)(1 << 14));      /* filter/dc_blocker.h:57 */
@@ -472,11 +972,20 @@ extern "C" int gpupager_create(gpupager_t **ph, const gpupager_cfg *cfg)
     h->res_pitch = (long long)((max_out + 63) & ~(size_t)63);
     PFAIL(cudaMalloc(&h->d_res, (size_t)C * h->res_pitch * sizeof(short)));
     PFAIL(cudaMalloc(&h->d_stage, (size_t)C * h->max_feed * sizeof(short)));
-    PFAIL(cudaMalloc(&h->d_states, (size_t)C * sizeof(PocsagState)));
-    PFAIL(cudaMemset(h->d_states, 0, (size_t)C * sizeof(PocsagState)));
-    PFAIL(cudaMalloc(&h->d_text, (size_t)C * 1024));
-    PFAIL(cudaMemset(h->d_text, 0, (size_t)C * 1024));
+    if (h->decoder == GPUPAGER_DECODER_FLEX) {
+        PFAIL(cudaMalloc(&h->d_fstates, (size_t)C * sizeof(FlexState)));
+        PFAIL(cudaMemset(h->d_fstates, 0, (size_t)C * sizeof(FlexState)));
+        flex_init_kernel<<<(C + 63) / 64, 64, 0, h->stream>>>(h->d_fstates, C);
+        PFAIL(cudaGetLastError());
+    } else {
+        PFAIL(cudaMalloc(&h->d_states, (size_t)C * sizeof(PocsagState)));
+        PFAIL(cudaMemset(h->d_states, 0, (size_t)C * sizeof(PocsagState)));
+        PFAIL(cudaMalloc(&h->d_text, (size_t)C * 1024));
+        PFAIL(cudaMemset(h->d_text, 0, (size_t)C * 1024));
+    }
     h->msg_cap = 32 + (uint32_t)(max_out / 1000);       /* shortest message: 2 codewords x 16 samples/bit */
+    if (h->decoder == GPUPAGER_DECODER_FLEX)
+        h->msg_cap = 384 + (uint32_t)(max_out / 80);    /* a block end can deliver every address of up to 4 phases at once */
     PFAIL(cudaMalloc(&h->d_msgs, (size_t)C * h->msg_cap * sizeof(gpupager_msg)));
     PFAIL(cudaMalloc(&h->d_count, C * sizeof(uint32_t)));
     PFAIL(cudaMemset(h->d_count, 0, C * sizeof(uint32_t)));
@@ -517,6 +1026,7 @@ static int pager_run(gpupager *h, const short *d_pcm, size_t pitch, size_t n, cu
         in.carry = h->d_carry[h->pp]; in.fresh = d_pcm;
         in.carry_pitch = h->carry_pitch; in.fresh_pitch = (long long)pitch;
         in.carry_len = h->carry_len; in.total = h->carry_len + (long long)n;
+        in.invert = (h->flags & GPUPAGER_F_INVERT) ? 1 : 0;
         const unsigned long long total = h->total_in + n;
         /* outputs m with n_m + M < total  <=>  m < (total - M) * I / D   (polyphase_fir.c:184, strict) */
         unsigned long long m_end = h->m_next;
@@ -552,6 +1062,17 @@ static int pager_run(gpupager *h, const short *d_pcm, size_t pitch, size_t n, cu
         h->carry_len = keep;
         h->in_base = n_next;
         dec_in = h->d_res; dec_pitch = h->res_pitch; nr_dec = (unsigned)nr_out;
+    } else if (h->flags & GPUPAGER_F_INVERT) {
+        /* no resampler to fold the negation into: a negated copy */
+        if (n > (size_t)h->res_pitch) return perr(GPUPAGER_E_INVAL, "feed too large");
+        InPcm in;
+        in.carry = nullptr; in.fresh = d_pcm; in.carry_pitch = 0; in.fresh_pitch = (long long)pitch;
+        in.carry_len = 0; in.total = (long long)n; in.invert = 1;
+        dim3 grid((unsigned)((n + 255) / 256), C);
+        pcm_carry_kernel<<<grid, 256, 0, st>>>(in, 0, h->d_res, h->res_pitch, (int)n);
+        h->launches++;
+        PCUDA(cudaGetLastError());
+        dec_in = h->d_res; dec_pitch = h->res_pitch;
     } else if (h->flags & (GPUPAGER_F_DC_BLOCK | GPUPAGER_F_KEEP_PCM)) {
         /* the decoder may rewrite samples in place (DC blocker) and the -d tap wants them: work on a copy */
         if (n > (size_t)h->res_pitch) return perr(GPUPAGER_E_INVAL, "feed too large");
@@ -562,8 +1083,12 @@ static int pager_run(gpupager *h, const short *d_pcm, size_t pitch, size_t n, cu
     h->last_out = nr_dec;
     if (nr_dec) {
         MsgSink sink{ h->d_msgs, h->d_count, h->d_dropped, h->msg_cap };
-        pocsag_kernel<<<(C + 31) / 32, 32, 0, st>>>(h->d_states, h->d_text, C, const_cast<short *>(dec_in), dec_pitch, nr_dec, sink,
-                                                    (h->flags & GPUPAGER_F_DC_BLOCK) ? 1 : 0, h->dc_p);
+        if (h->decoder == GPUPAGER_DECODER_FLEX)
+            flex_kernel<<<(C + 31) / 32, 32, 0, st>>>(h->d_fstates, C, const_cast<short *>(dec_in), dec_pitch, nr_dec, sink,
+                                                      (h->flags & GPUPAGER_F_DC_BLOCK) ? 1 : 0, h->dc_p);
+        else
+            pocsag_kernel<<<(C + 31) / 32, 32, 0, st>>>(h->d_states, h->d_text, C, const_cast<short *>(dec_in), dec_pitch, nr_dec, sink,
+                                                        (h->flags & GPUPAGER_F_DC_BLOCK) ? 1 : 0, h->dc_p);
         h->launches++;
         PCUDA(cudaGetLastError());
     }
@@ -639,8 +1164,30 @@ extern "C" int gpupager_dispatch(gpupager_t *h, gpupager_on_msg_func_t on_numeri
     if (!h) return perr(GPUPAGER_E_BADARGS, "null handle");
     if (int rc = pager_drain(h)) return rc;
     for (const gpupager_msg &m : h->queue) {
+        if (m.kind != GPUPAGER_MSG_ALPHA && m.kind != GPUPAGER_MSG_NUMERIC) continue;
         gpupager_on_msg_func_t cb = (m.kind == GPUPAGER_MSG_ALPHA) ? on_alpha : on_numeric;
         if (cb) cb(user, m.channel, (uint16_t)m.baud, m.capcode, m.text, m.len, (uint8_t)m.function);
+    }
+    if (nr_msgs) *nr_msgs = h->queue.size();
+    h->queue.clear();
+    return GPUPAGER_OK;
+}
+
+extern "C" int gpupager_dispatch_flex(gpupager_t *h, gpupager_on_flex_alnum_func_t on_alnum, gpupager_on_flex_num_func_t on_num,
+                                      gpupager_on_flex_siv_func_t on_siv, void *user, size_t *nr_msgs)
+{
+    if (!h) return perr(GPUPAGER_E_BADARGS, "null handle");
+    if (int rc = pager_drain(h)) return rc;
+    for (const gpupager_msg &m : h->queue) {
+        const uint64_t cap = (uint64_t)m.capcode | ((uint64_t)m.capcode_hi << 32);
+        if (m.kind == GPUPAGER_MSG_FLEX_ALNUM && on_alnum)
+            on_alnum(user, m.channel, (uint16_t)m.baud, (uint8_t)m.function, (uint8_t)m.aux[0], (uint8_t)m.aux[1], cap,
+                     (int)m.aux[2], (int)m.aux[3], (uint8_t)m.aux[4], m.text, m.len);
+        else if (m.kind == GPUPAGER_MSG_FLEX_NUM && on_num)
+            on_num(user, m.channel, (uint16_t)m.baud, (uint8_t)m.function, (uint8_t)m.aux[0], (uint8_t)m.aux[1], cap, m.text, m.len);
+        else if (m.kind == GPUPAGER_MSG_FLEX_SIV && on_siv)
+            on_siv(user, m.channel, (uint16_t)m.baud, (uint8_t)m.function, (uint8_t)m.aux[0], (uint8_t)m.aux[1], cap,
+                   (uint8_t)m.aux[2], m.aux[3]);
     }
     if (nr_msgs) *nr_msgs = h->queue.size();
     h->queue.clear();

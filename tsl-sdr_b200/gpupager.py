@@ -7,7 +7,9 @@ import numpy as np
 
 from . import _lib
 
-F_DC_BLOCK, F_KEEP_PCM, F_NO_RESAMPLE = 0x1, 0x2, 0x4
+F_DC_BLOCK, F_KEEP_PCM, F_NO_RESAMPLE, F_INVERT = 0x1, 0x2, 0x4, 0x8
+DECODER_POCSAG, DECODER_FLEX = 0, 1
+MSG_NUMERIC, MSG_ALPHA, MSG_FLEX_ALNUM, MSG_FLEX_NUM, MSG_FLEX_SIV = 0, 1, 2, 3, 4
 
 
 class GpuPagerError(RuntimeError):
@@ -31,7 +33,7 @@ def quantize_taps(coeffs):
 
 class GpuPager:
     def __init__(self, nr_channels, max_feed_samples, taps_q14=None, interpolate=1, decimate=1, device=0, flags=0,
-                 dc_pole=0.9999):
+                 dc_pole=0.9999, decoder=DECODER_POCSAG):
         L = self._L = _lib.lib()
         cfg = _lib.GpuPagerCfg()
         cfg.struct_size = C.sizeof(_lib.GpuPagerCfg)
@@ -45,6 +47,7 @@ class GpuPager:
         cfg.flags = int(flags)
         cfg.dc_pole = float(dc_pole)
         cfg.taps = None if self._taps is None else self._taps.ctypes.data_as(C.POINTER(C.c_int16))
+        cfg.decoder = int(decoder)
         self._h = C.c_void_p()
         _check(L.gpupager_create(C.byref(self._h), C.byref(cfg)), "gpupager_create")
         self.nr_channels = int(nr_channels)
@@ -78,6 +81,39 @@ class GpuPager:
             raw = C.string_at(C.addressof(m) + _lib.GpuPagerMsg.text.offset, min(m.len, 512))
             out.append((m.channel, m.kind, m.baud, m.capcode, m.function, m.len, raw))
         return out
+
+    def poll_full(self, cap=4096):
+        """Records in the oracle's tuple shape: (channel, (kind, baud, capcode64, function, len, aux, text))."""
+        arr = (_lib.GpuPagerMsg * cap)()
+        n = C.c_size_t(0)
+        _check(self._L.gpupager_poll(self._h, arr, cap, C.byref(n)), "gpupager_poll")
+        out = []
+        for i in range(n.value):
+            m = arr[i]
+            raw = C.string_at(C.addressof(m) + _lib.GpuPagerMsg.text.offset, min(m.len, 512))
+            out.append((m.channel, (m.kind, m.baud, m.capcode | (m.capcode_hi << 32), m.function, m.len, tuple(m.aux), raw)))
+        return out
+
+    def dispatch_flex(self):
+        """Fires the three C callbacks of pager/pager_flex.h and returns what they received, as oracle-shaped tuples."""
+        got = []
+
+        def on_alnum(user, channel, baud, phase, cycle, frame, cap, fragmented, maildrop, seq, data, length):
+            got.append((channel, (2, baud, cap, phase, length, (cycle, frame, fragmented, maildrop, seq, 0), C.string_at(data, length))))
+            return 0
+
+        def on_num(user, channel, baud, phase, cycle, frame, cap, data, length):
+            got.append((channel, (3, baud, cap, phase, length, (cycle, frame, 0, 0, 0, 0), C.string_at(data, length))))
+            return 0
+
+        def on_siv(user, channel, baud, phase, cycle, frame, cap, siv_type, data):
+            got.append((channel, (4, baud, cap, phase, 0, (cycle, frame, siv_type, data, 0, 0), b"")))
+            return 0
+        a, b, c = _lib.ON_FLEX_ALNUM(on_alnum), _lib.ON_FLEX_NUM(on_num), _lib.ON_FLEX_SIV(on_siv)
+        n = C.c_size_t(0)
+        _check(self._L.gpupager_dispatch_flex(self._h, a, b, c, None, C.byref(n)), "gpupager_dispatch_flex")
+        assert n.value == len(got)
+        return got
 
     def dispatch(self):
         """Fires the C callbacks (same argument meaning as pager/pager_pocsag.h) and returns what they received."""
