@@ -11,6 +11,7 @@
 #include <stdatomic.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -118,6 +119,60 @@ static int on_numeric(void *user, uint32_t ch, uint16_t baud, uint32_t cap, cons
     return on_pocsag_msg(user, "numeric", ch, baud, cap, d, n, fn);
 }
 
+/* ---- FLEX JSON lines: decoder/decoder.c:173-262 (same keys, same order, plus "channel") ---- */
+static const char flex_phase_id[4] = { 'A', 'B', 'C', 'D' };
+
+static void flex_head(struct receiver *rx, const char *type, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no,
+                      uint8_t frame_no, uint64_t cap_code)
+{
+    time_t now = time(NULL);
+    struct tm gmt;
+    gmtime_r(&now, &gmt);
+    fprintf(rx->msg_out, "{\"proto\":\"flex\",\"type\":\"%s\",\"timestamp\":\"%04i-%02i-%02i %02i:%02i:%02i UTC\","
+            "\"baud\":%i,\"syncLevel\":%i,\"frameNo\":%u,\"cycleNo\":%u,\"phaseNo\":\"%c\",\"capCode\":%llu,\"channel\":%u,",
+            type, gmt.tm_year + 1900, gmt.tm_mon + 1, gmt.tm_mday, gmt.tm_hour, gmt.tm_min, gmt.tm_sec,
+            baud, 0, frame_no, cycle_no, flex_phase_id[phase & 3], (unsigned long long)cap_code, channel);
+}
+
+static int on_flex_alnum(void *user, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no, uint8_t frame_no,
+                         uint64_t cap_code, int fragmented, int maildrop, uint8_t seq_num, const char *msg, size_t len)
+{
+    struct receiver *rx = user;
+    flex_head(rx, "alphanumeric", channel, baud, phase, cycle_no, frame_no, cap_code);
+    fprintf(rx->msg_out, "\"fragment\":%s,\"maildrop\":%s,\"fragSeq\":%u,\"message\":\"", fragmented ? "true" : "false",
+            maildrop ? "true" : "false", seq_num);
+    for (size_t i = 0; i < len; i++) put_alnum_char(rx->msg_out, msg[i]);
+    fputs("\"}\n", rx->msg_out);
+    fflush(rx->msg_out);
+    rx->nr_messages++;
+    return 0;
+}
+
+static int on_flex_num(void *user, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no, uint8_t frame_no,
+                       uint64_t cap_code, const char *msg, size_t len)
+{
+    struct receiver *rx = user;
+    flex_head(rx, "numeric", channel, baud, phase, cycle_no, frame_no, cap_code);
+    fputs("\"message\":\"", rx->msg_out);
+    for (size_t i = 0; i < len; i++) put_alnum_char(rx->msg_out, msg[i]);
+    fputs("\"}\n", rx->msg_out);
+    fflush(rx->msg_out);
+    rx->nr_messages++;
+    return 0;
+}
+
+static int on_flex_siv(void *user, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no, uint8_t frame_no,
+                       uint64_t cap_code, uint8_t siv_msg_type, uint32_t data)
+{
+    struct receiver *rx = user;
+    if (siv_msg_type != 0) return 0;            /* decoder.c:249-257 prints temporary address activations only */
+    flex_head(rx, "tempAddrActivation", channel, baud, phase, cycle_no, frame_no, cap_code);
+    fprintf(rx->msg_out, "\"startFrameNo\":%u,\"tempAddressId\":%u}\n", data & 0x7f, (data >> 7) & 0xf);
+    fflush(rx->msg_out);
+    rx->nr_messages++;
+    return 0;
+}
+
 /* ---- consumer: batch sample_bufs into pinned memory, submit, collect the previous batch, write FIFOs ---- */
 static void write_outputs(struct receiver *rx, size_t n_out)
 {
@@ -179,7 +234,8 @@ static void submit_batch(struct receiver *rx)
             abort();
         }
         size_t nr = 0;
-        gpupager_dispatch(rx->pager, on_numeric, on_alpha, rx, &nr);
+        if (rx->pager_is_flex) gpupager_dispatch_flex(rx->pager, on_flex_alnum, on_flex_num, on_flex_siv, rx, &nr);
+        else gpupager_dispatch(rx->pager, on_numeric, on_alpha, rx, &nr);
     }
     rx->in_flight++;
     rx->batch_cur ^= 1;
@@ -334,6 +390,13 @@ aresult_t receiver_init(struct receiver *rx, const jnode *cfg, receiver_rx_threa
         pc.max_feed_samples = (uint32_t)rx->pcm_cap; pc.taps = q;
         double pole = 0.0;
         if (!json_get_double(pd, "dcBlockPole", &pole)) { pc.flags |= GPUPAGER_F_DC_BLOCK; pc.dc_pole = pole; }
+        const char *proto = NULL;                           /* decoder -m POCSAG | FLEX */
+        if (!json_get_string(pd, "protocol", &proto) && !strncasecmp(proto, "flex", 4)) {
+            pc.decoder = GPUPAGER_DECODER_FLEX;
+            rx->pager_is_flex = true;
+        }
+        int inv = 0;                                        /* decoder -i */
+        if (!json_get_int(pd, "invert", &inv) && inv) pc.flags |= GPUPAGER_F_INVERT;
         gpupager_t *pg = NULL;
         rc = gpupager_create(&pg, &pc);
         free(cf); free(q);

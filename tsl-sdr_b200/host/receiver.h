@@ -55,6 +55,7 @@ struct receiver {
     /* GPU consumer */
     struct gpuchan *bank;
     struct gpupager *pager;
+    bool pager_is_flex;                 /* pagerDecode.protocol == "flex" (decoder -m FLEX) */
     int gpu_device;
     size_t batch_bufs;                  /* sample_bufs per GPU submit (gpuBatchBuffers, default 64) */
     int16_t *batch[2];                  /* pinned staging, double buffered */
