@@ -83,6 +83,18 @@ int gpuchan_destroy(gpuchan_t **ph);
  * only if it is pageable (pinned buffers must stay untouched until gpuchan_sync/collect). */
 int gpuchan_submit(gpuchan_t *h, const int16_t *iq_host, size_t n_complex);
 
+/* 8-bit captures: the bytes cross PCIe as they are (half the traffic of cs16) and are widened on the device with
+ * the reference's own conversions:
+ *   GPUCHAN_FMT_CS8     (int16_t)(int8_t)b                       multifm/file_if.c:67-110  (fileFormat "cs8")
+ *   GPUCHAN_FMT_CU8     (int16_t)(int8_t)b - 127                 multifm/file_if.c:112-157 (fileFormat "cu8"; the
+ *                       reference reads the unsigned bytes through an int8_t pointer -- reproduced as is)
+ *   GPUCHAN_FMT_CU8_RTL ((int16_t)(uint8_t)b - 127) << 7         multifm/rtl_sdr_if.c:142-147 (live RTL-SDR contract)
+ * iq8_host holds 2 * n_complex bytes (I, Q interleaved).  Otherwise identical to gpuchan_submit. */
+#define GPUCHAN_FMT_CS8     1u
+#define GPUCHAN_FMT_CU8     2u
+#define GPUCHAN_FMT_CU8_RTL 3u
+int gpuchan_submit_bytes(gpuchan_t *h, const uint8_t *iq8_host, size_t n_complex, uint32_t format);
+
 /* Same, with the samples already resident on h's device (e.g. after an NCCL broadcast).  cuda_stream
  * (a cudaStream_t) only tells WHEN d_iq becomes readable: the bank waits for that stream's current position and
  * then works on its own streams, so the producer of batch i+1 overlaps the kernels of batch i.  NULL = readable

@@ -200,3 +200,34 @@ def test_auto_engine_picks_tensor_cores_for_wide_banks():
     b = GpuChan(lpf, synth.channel_offsets(3, fs), fs, D, 1 << 16)
     assert a.engine == ENGINE_TC and b.engine == ENGINE_IMAD
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("fmt_name", ["cs8", "cu8", "cu8_rtl"])
+def test_8bit_formats_widened_on_device(oracle, fmt_name):
+    """f3: 8-bit captures cross PCIe as bytes and are widened on the device with the reference's conversions
+    (multifm/file_if.c:67-157, multifm/rtl_sdr_if.c:142-147, including the cu8 int8_t-pointer quirk)."""
+    from tsl_sdr_b200.gpuchan import FMT_CS8, FMT_CU8, FMT_CU8_RTL
+    C, T, D, fs = 40, 127, 50, 2400000
+    n = 60000
+    raw = np.random.default_rng(21).integers(0, 256, 2 * n, dtype=np.uint8)
+    if fmt_name == "cs8":
+        fmt, wide = FMT_CS8, raw.view(np.int8).astype(np.int16)
+    elif fmt_name == "cu8":
+        fmt, wide = FMT_CU8, (raw.view(np.int8).astype(np.int16) - 127).astype(np.int16)
+    else:
+        fmt, wide = FMT_CU8_RTL, ((raw.astype(np.int16) - 127) << 7).astype(np.int16)
+    lpf = synth.lowpass_taps(T, 60000.0, fs)
+    offs = synth.channel_offsets(C, fs)
+    gains = np.full(C, 8.0)
+    exp_pcm, _ = oracle_bank(oracle, lpf, offs, fs, D, wide, gains=gains)
+    for engine in (ENGINE_IMAD, ENGINE_TC):
+        bank = GpuChan(lpf, offs, fs, D, 25000, gains=gains, flags=F_ATAN_FMA, engine=engine)
+        got, pos = [], 0
+        for k in (25000, 4096, 1, 25000, 5903):
+            bank.submit_bytes(raw[2 * pos: 2 * (pos + k)], fmt)
+            got.append(bank.collect().copy())
+            pos += k
+        bank.close()
+        assert pos == n
+        got = np.concatenate(got, axis=1)
+        assert got.shape == exp_pcm.shape and np.array_equal(got, exp_pcm)

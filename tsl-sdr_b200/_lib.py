@@ -43,6 +43,7 @@ def _declare(L: C.CDLL) -> None:
     L.gpuchan_destroy.argtypes = [C.POINTER(vp)]
     L.gpuchan_submit.argtypes = [vp, vp, sz]
     L.gpuchan_submit_device.argtypes = [vp, vp, sz, vp]
+    L.gpuchan_submit_bytes.argtypes = [vp, vp, sz, C.c_uint32]
     L.gpuchan_sync.argtypes = [vp]
     L.gpuchan_stream_wait.argtypes = [vp, vp]
     L.gpuchan_pending.argtypes = [vp, C.POINTER(sz)]
@@ -104,7 +105,7 @@ ON_MSG = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint32, C.
 
 # every symbol include/tslb200_gpuchan.h declares (checked by the CPU test-suite)
 EXPORTS = ["gpuchan_prepare_taps", "gpuchan_derot_increment", "gpuchan_db_to_gain", "gpuchan_create",
-           "gpuchan_destroy", "gpuchan_submit", "gpuchan_submit_device", "gpuchan_sync", "gpuchan_pending",
+           "gpuchan_destroy", "gpuchan_submit", "gpuchan_submit_device", "gpuchan_submit_bytes", "gpuchan_sync", "gpuchan_pending",
            "gpuchan_collect", "gpuchan_collect_iq", "gpuchan_device_pcm", "gpuchan_get_taps",
            "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error", "gpuchan_timing_enable", "gpuchan_in_flight", "gpuchan_discard", "gpuchan_host_alloc", "gpuchan_host_free", "gpuchan_tc_selftest", "gpuchan_debug_stamps", "gpuchan_stream_wait",
            "gpuchan_timing_read",

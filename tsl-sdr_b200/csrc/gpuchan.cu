@@ -22,6 +22,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <complex>
 #include <cstdarg>
 #include <cmath>
@@ -386,6 +387,19 @@ __global__ void carry_save_kernel(InWindow in, long long from, int *__restrict__
     if (i < n) dst[i] = in_sample(in, from + i);
 }
 
+/* 8-bit I,Q bytes -> packed int16 pairs, with the reference's conversions (see gpuchan_submit_bytes) */
+__global__ void widen_bytes_kernel(const uchar2 *__restrict__ src, int *__restrict__ dst, size_t n, unsigned format)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uchar2 b = src[i];
+        int re, im;
+        if (format == GPUCHAN_FMT_CS8)      { re = (int)(signed char)b.x;        im = (int)(signed char)b.y; }
+        else if (format == GPUCHAN_FMT_CU8) { re = (int)(signed char)b.x - 127;  im = (int)(signed char)b.y - 127; }
+        else                                { re = ((int)b.x - 127) << 7;        im = ((int)b.y - 127) << 7; }
+        dst[i] = pack16(re, im);
+    }
+}
+
 template <int CPT, int R>
 size_t imad_smem_bytes(int T, int D)
 {
@@ -420,6 +434,7 @@ struct gpuchan {
     int *d_carry[2] = { nullptr, nullptr };
     static constexpr int NSLOT = 2;          /* batches in flight: H2D | kernels | D2H overlap */
     int *d_stage[NSLOT] = { nullptr, nullptr };
+    uint8_t *d_stage8[NSLOT] = { nullptr, nullptr };    /* 8-bit staging, allocated on first gpuchan_submit_bytes */
     int *d_ckpt = nullptr;
     size_t ckpt_tiles = 0;
     float2 *d_atan = nullptr;
@@ -489,7 +504,7 @@ static int free_all(gpuchan *h)
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     if (h->s_pre) cudaStreamDestroy(h->s_pre);
     for (int i = 0; i < gpuchan::NSLOT; i++) {
-        cudaFree(h->d_stage[i]); cudaFree(h->d_pcm[i]); cudaFree(h->d_iq[i]);
+        cudaFree(h->d_stage[i]); cudaFree(h->d_stage8[i]); cudaFree(h->d_pcm[i]); cudaFree(h->d_iq[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
@@ -891,6 +906,30 @@ extern "C" int gpuchan_submit(gpuchan_t *h, const int16_t *iq_host, size_t n_com
      * The staging slot was last read by the kernels of batch i-2 (ev_done of this slot). */
     CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));
     if (n_complex) CUDA_TRY(cudaMemcpyAsync(h->d_stage[slot], iq_host, n_complex * 4, cudaMemcpyHostToDevice, h->s_in));
+    CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
+    return run_batch(h, h->d_stage[slot], n_complex, h->stream, slot, h->ev_h2d[slot]);
+}
+
+extern "C" int gpuchan_submit_bytes(gpuchan_t *h, const uint8_t *iq8_host, size_t n_complex, uint32_t format)
+{
+    if (!h || (!iq8_host && n_complex)) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    if (format != GPUCHAN_FMT_CS8 && format != GPUCHAN_FMT_CU8 && format != GPUCHAN_FMT_CU8_RTL)
+        return set_err(GPUCHAN_E_BADARGS, "unknown sample format %u", format);
+    if (n_complex > h->max_batch) return set_err(GPUCHAN_E_INVAL, "submit of %zu samples exceeds max_batch_samples %zu", n_complex, h->max_batch);
+    if (int rc = slot_acquire(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int slot = (int)(h->submit_seq % gpuchan::NSLOT);
+    if (!h->d_stage8[slot]) CUDA_TRY(cudaMalloc(&h->d_stage8[slot], h->max_batch * 2));
+    /* same overlap as gpuchan_submit: copy + widen of batch i on the input stream while batch i-1 computes */
+    CUDA_TRY(cudaStreamWaitEvent(h->s_in, h->ev_done[slot], 0));
+    if (n_complex) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_stage8[slot], iq8_host, n_complex * 2, cudaMemcpyHostToDevice, h->s_in));
+        const unsigned blocks = (unsigned)std::min<size_t>((n_complex + 255) / 256, (size_t)h->nr_sms * 8);
+        widen_bytes_kernel<<<blocks, 256, 0, h->s_in>>>(reinterpret_cast<const uchar2 *>(h->d_stage8[slot]), h->d_stage[slot],
+                                                        n_complex, format);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     CUDA_TRY(cudaEventRecord(h->ev_h2d[slot], h->s_in));
     return run_batch(h, h->d_stage[slot], n_complex, h->stream, slot, h->ev_h2d[slot]);
 }

@@ -9,6 +9,7 @@ from . import _lib
 
 F_ATAN_FMA = 0x1
 F_KEEP_IQ = 0x2
+FMT_CS8, FMT_CU8, FMT_CU8_RTL = 1, 2, 3      # gpuchan_submit_bytes formats (include/tslb200_gpuchan.h)
 ENGINE_AUTO, ENGINE_IMAD, ENGINE_TC = 0, 1, 2
 
 
@@ -93,6 +94,12 @@ class GpuChan:
 
     def submit_ptr(self, host_ptr: int, n_complex: int):
         _check(self._L.gpuchan_submit(self._h, host_ptr, n_complex), "gpuchan_submit")
+
+    def submit_bytes(self, iq8: np.ndarray, fmt: int):
+        """8-bit interleaved I,Q (uint8 view), widened on the device: FMT_CS8 / FMT_CU8 / FMT_CU8_RTL."""
+        iq8 = np.ascontiguousarray(iq8).view(np.uint8)
+        self._keep8 = iq8
+        _check(self._L.gpuchan_submit_bytes(self._h, iq8.ctypes.data, len(iq8) // 2, int(fmt)), "gpuchan_submit_bytes")
 
     def submit_device(self, dev_ptr: int, n_complex: int, stream: int = 0):
         _check(self._L.gpuchan_submit_device(self._h, dev_ptr, n_complex, stream), "gpuchan_submit_device")

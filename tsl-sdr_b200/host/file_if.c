@@ -52,6 +52,10 @@ static aresult_t file_worker_thread_work(struct receiver *rx)
             nr = read_full(thr->fd, thr->bounce, SAMPLES_PER_BUF * 2);
             for (ssize_t i = 0; i < nr; i++)
                 out[i] = (thr->fmt == FMT_CS8) ? (int16_t)thr->bounce[i] : (int16_t)((int16_t)thr->bounce[i] - 127);
+            /* file_if.c:147-151: a read that is not a multiple of 4 bytes (only at the end of a file) leaves its last
+             * nr % 4 cu8 values without the -127 offset */
+            if (thr->fmt == FMT_CU8)
+                for (ssize_t i = nr - nr % 4; i < nr; i++) out[i] = (int16_t)thr->bounce[i];
             if (nr > 0) sbuf->nr_samples = (uint32_t)(nr / 2);
         }
         if (nr <= 0 || sbuf->nr_samples == 0) {     /* EOF: the reference aborts here (receiver.c:84) */
