@@ -122,6 +122,23 @@ int gpupager_poll(gpupager_t *h, gpupager_msg *out, size_t cap, size_t *nr_msgs)
 /* decoder -d tap: resampled PCM of the last feed, channel c at out[c*cap ...]; needs GPUPAGER_F_KEEP_PCM. */
 int gpupager_collect_pcm(gpupager_t *h, int16_t *out, size_t cap_per_channel, size_t *n_per_channel);
 
+/* ---- Mueller-Muller soft-decision timing recovery (pager/mueller_muller.c:10-115) for every channel ----
+ * The reference ships this block but wires it into no pipeline (mm_init/mm_process have no callers); it is offered
+ * here as an optional pre-slicer with the same parameters, state and outputs.  One state per channel; every call
+ * consumes n samples per channel (channel c at pcm_host + c*pitch) and appends the decisions (the samples picked
+ * at the recovered symbol instants) to decisions_host + c*cap, reporting their number in nr_out[c].
+ * GPUMM_F_FMA selects the contraction GNU C applies to mueller_muller.c:79,92 on FMA machines (the reference's
+ * Release build); without it every multiply and add rounds separately. */
+#define GPUMM_F_FMA 0x1u
+typedef struct gpumm gpumm_t;
+int gpumm_create(gpumm_t **ph, uint32_t nr_channels, int32_t device, float kw, float km, float samples_per_bit,
+                 float error_min, float error_max, uint32_t max_feed_samples, uint32_t flags);
+int gpumm_process(gpumm_t *h, const int16_t *pcm_host, size_t pitch_samples, size_t n, int16_t *decisions_host,
+                  size_t cap_per_channel, uint32_t *nr_out);
+/* mm_process state of one channel after the last call: {w, m, next_offset, last_sample} */
+int gpumm_get_state(gpumm_t *h, uint32_t channel, float state[4]);
+int gpumm_destroy(gpumm_t **ph);
+
 uint64_t gpupager_kernel_launches(gpupager_t *h);
 uint64_t gpupager_dropped_msgs(gpupager_t *h);
 const char *gpupager_last_error(void);

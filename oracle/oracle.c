@@ -1009,3 +1009,39 @@ void orc_flex_on_pcm(orc_flex *f, const int16_t *pcm, size_t n)                 
         }
     }
 }
+
+/* ---------------------------------------------------------------------- */
+/* f4  Mueller-Muller timing recovery: pager/mueller_muller.c:10-115        */
+/* (dead code in the reference's pipelines -- SURVEY.md F5 -- restated for  */
+/* the standalone differential test).  fma = 1 reproduces what GNU C's      */
+/* default -ffp-contract=fast makes of :80 and :95 on an FMA machine.       */
+/* ---------------------------------------------------------------------- */
+void orc_mm_init(orc_mm *mm, float kw, float km, float samples_per_bit, float error_min, float error_max)
+{
+    memset(mm, 0, sizeof(*mm));
+    mm->w = mm->m = samples_per_bit;                            /* :19-20 */
+    mm->kw = kw; mm->km = km; mm->error_min = error_min; mm->error_max = error_max;
+}
+
+static float mm_sign(float v) { return (float)(v > 0) - (float)(v < 0); }      /* :34-38 */
+
+size_t orc_mm_process(orc_mm *mm, const int16_t *samples, size_t n, int16_t *decisions, size_t cap, int fma)
+{
+    float cur = mm->next_offset, w = mm->w, m = mm->m;
+    const float nf = (float)n;
+    size_t nd = 0;
+    while (cur < nf && nd < cap) {                              /* :65 */
+        const float sample = samples[(size_t)(cur + 0.5f)];     /* :66 */
+        decisions[nd++] = (int16_t)sample;                      /* :70 */
+        const float w_error = mm_sign(mm->last_sample) * sample - mm_sign(sample) * mm->last_sample;   /* :76, exact */
+        if (fma) w = fmaf(w_error, mm->kw, w); else w += w_error * mm->kw;                             /* :79 */
+        if (mm->error_min > w) w = mm->error_min; else if (mm->error_max < w) w = mm->error_max;       /* :86-90 */
+        if (fma) m += fmaf(mm->km, sample, w); else m += w + mm->km * sample;                          /* :92 */
+        cur += floorf(m);                                       /* :95 */
+        m -= floorf(m);
+        mm->last_sample = sample;
+    }
+    mm->next_offset = cur - nf;                                 /* :107-109 */
+    mm->w = w; mm->m = m;
+    return nd;
+}

@@ -87,6 +87,9 @@ class Oracle:
         L.orc_pocsag_msgs.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Msg))]
         L.orc_msg_size.restype = C.c_size_t
         assert L.orc_msg_size() == C.sizeof(Msg)
+        L.orc_mm_init.argtypes = [C.c_void_p] + [C.c_float] * 5
+        L.orc_mm_process.restype = C.c_size_t
+        L.orc_mm_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
         L.orc_flex_new.restype = C.c_void_p
         L.orc_flex_new.argtypes = [C.c_size_t]
         L.orc_flex_delete.argtypes = [C.c_void_p]
@@ -175,6 +178,21 @@ class Oracle:
         return msgs
 
 
+    # f4
+    def mm(self, pcm, kw, km, spb, emin, emax, chunk=0, fma=1):
+        """Returns (decisions int16, final state (w, m, next_offset, last_sample) as float32)."""
+        pcm = _as_i16(pcm)
+        st = (C.c_float * 8)()
+        self.L.orc_mm_init(st, kw, km, spb, emin, emax)
+        n = len(pcm)
+        chunk = chunk or n
+        out = np.zeros(n + 16, np.int16)
+        tot = 0
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            tot += self.L.orc_mm_process(st, pcm[s:e].ctypes.data, e - s, out[tot:].ctypes.data, len(out) - tot, int(fma))
+        return out[:tot].copy(), np.array(list(st)[4:8], dtype=np.float32)
+
     # a8
     def flex(self, pcm, chunk=0, max_msgs=4096):
         pcm = _as_i16(pcm)
@@ -256,6 +274,9 @@ class Ref:
         L.ref_pocsag_msgs.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Msg)), C.POINTER(C.c_size_t)]
         L.ref_decoder_pocsag_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.ref_msg_size.restype = C.c_size_t
+        if hasattr(L, "ref_mm_run"):
+            L.ref_mm_run.restype = C.c_size_t
+            L.ref_mm_run.argtypes = [C.c_float] * 5 + [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
         L.ref_bch_decode.argtypes = [C.POINTER(C.c_uint32)]
         L.ref_flex_new.restype = C.c_void_p
         L.ref_flex_new.argtypes = [C.c_uint32, C.c_size_t]
@@ -360,6 +381,13 @@ class Ref:
         self.L.ref_pocsag_delete(p)
         self.L.ref_resamp_delete(r)
         return msgs
+
+    def mm(self, pcm, kw, km, spb, emin, emax, chunk=0):
+        pcm = _as_i16(pcm)
+        out = np.zeros(len(pcm) + 16, np.int16)
+        st = np.zeros(4, np.float32)
+        n = self.L.ref_mm_run(kw, km, spb, emin, emax, pcm.ctypes.data, len(pcm), chunk, out.ctypes.data, len(out), st.ctypes.data)
+        return out[:n].copy(), st
 
     def flex(self, pcm, chunk=0, max_msgs=4096):
         pcm = _as_i16(pcm)

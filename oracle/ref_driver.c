@@ -32,6 +32,7 @@
 #include <pager/pager.h>
 #include <pager/pager_pocsag.h>
 #include <pager/pager_flex.h>
+#include <pager/mueller_muller.h>
 #include <pager/bch_code.h>
 
 #include <tsl/assert.h>
@@ -543,6 +544,26 @@ size_t ref_flex_msgs(void *h, struct ref_msg **pmsgs, size_t *dropped)
     *pmsgs = r->mb.msgs;
     if (dropped) *dropped = r->mb.dropped;
     return r->mb.n;
+}
+
+/* ------------------------------------------------------------------ */
+/* f4: Mueller-Muller timing recovery (pager/mueller_muller.c; not wired */
+/* into any reference pipeline, tested standalone)                       */
+/* ------------------------------------------------------------------ */
+size_t ref_mm_run(float kw, float km, float samples_per_bit, float error_min, float error_max,
+                  const int16_t *pcm, size_t n, size_t chunk, int16_t *decisions, size_t cap, float state_out[4])
+{
+    struct mueller_muller mm;
+    TSL_BUG_IF_FAILED(mm_init(&mm, kw, km, samples_per_bit, error_min, error_max));
+    size_t total = 0;
+    if (chunk == 0) chunk = n;
+    while (n != 0) {
+        size_t take = n < chunk ? n : chunk, got = 0;
+        TSL_BUG_IF_FAILED(mm_process(&mm, pcm, take, decisions + total, cap - total, &got));
+        total += got; pcm += take; n -= take;
+    }
+    state_out[0] = mm.w; state_out[1] = mm.m; state_out[2] = mm.next_offset; state_out[3] = mm.last_sample;
+    return total;
 }
 
 /* ------------------------------------------------------------------ */

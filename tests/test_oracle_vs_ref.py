@@ -159,3 +159,34 @@ def test_random_pcm_into_flex(oracle, ref):
         for pos in range(3000, 280000, 50000):
             pcm[pos:pos + len(burst)] = burst
         assert oracle.flex(pcm) == ref.flex(pcm)
+
+
+def mm_signal(seed, spb=32.0, nbits=2500, jitter=0.002):
+    """NRZ at a slightly wrong symbol rate, smoothed, with noise: something for the timing loop to track."""
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 2, nbits)
+    t = np.arange(int(nbits * spb * (1 + jitter)) - 64) / (spb * (1 + jitter))
+    x = (1 - 2 * bits[t.astype(np.int64)]).astype(np.float64) * 6000
+    x = np.convolve(x, np.ones(9) / 9, mode="same") + rng.normal(0, 400, len(x))
+    return np.clip(np.round(x), -32768, 32767).astype(np.int16)
+
+
+MM_GAINS = [(1e-6, 1e-7), (3e-5, 2e-6), (1e-4, 1e-5), (0.0, 0.0)]
+
+
+@pytest.mark.parametrize("kw,km", MM_GAINS)
+def test_mueller_muller(oracle, kw, km):
+    """f4: pager/mueller_muller.c against the restatement, with and without GNU C's FMA contraction, chunked too."""
+    import pyoracle
+    if not pyoracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    pcm = mm_signal(3)
+    spb = 32.0
+    for variant, fma in (("fma", 1), ("nofma", 0)):
+        r = pyoracle.Ref(variant)
+        exp, st = r.mm(pcm, kw, km, spb, spb * 0.9, spb * 1.1)
+        got, gst = oracle.mm(pcm, kw, km, spb, spb * 0.9, spb * 1.1, fma=fma)
+        assert len(exp) > 2000 and np.array_equal(exp, got) and np.array_equal(st, gst)
+        got, gst = oracle.mm(pcm, kw, km, spb, spb * 0.9, spb * 1.1, chunk=1000, fma=fma)
+        exp2, st2 = r.mm(pcm, kw, km, spb, spb * 0.9, spb * 1.1, chunk=1000)
+        assert np.array_equal(exp2, got) and np.array_equal(st2, gst) and np.array_equal(exp2, exp)

@@ -1,1 +1,1 @@
-timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q -k "8bit" 2>&1 | tail -15
+timeout 1200 python -m pytest tests/test_gpu_pager.py -x -q -k "mueller" 2>&1 | tail -15

@@ -71,6 +71,10 @@ def _declare(L: C.CDLL) -> None:
     L.gpupager_dropped_msgs.restype = C.c_uint64
     L.gpupager_dropped_msgs.argtypes = [vp]
     L.gpupager_last_error.restype = C.c_char_p
+    L.gpumm_create.argtypes = [C.POINTER(vp), C.c_uint32, C.c_int32] + [C.c_float] * 5 + [C.c_uint32, C.c_uint32]
+    L.gpumm_process.argtypes = [vp, vp, sz, sz, vp, sz, vp]
+    L.gpumm_get_state.argtypes = [vp, C.c_uint32, vp]
+    L.gpumm_destroy.argtypes = [C.POINTER(vp)]
     L.gpuchan_in_flight.argtypes = [vp]
     L.gpuchan_host_alloc.argtypes = [C.POINTER(vp), sz]
     L.gpuchan_host_free.argtypes = [vp]
@@ -111,4 +115,5 @@ EXPORTS = ["gpuchan_prepare_taps", "gpuchan_derot_increment", "gpuchan_db_to_gai
            "gpuchan_timing_read",
            "gpupager_quantize_taps", "gpupager_create", "gpupager_destroy", "gpupager_feed_device", "gpupager_feed",
            "gpupager_dispatch", "gpupager_dispatch_flex", "gpupager_poll", "gpupager_collect_pcm", "gpupager_kernel_launches",
-           "gpupager_dropped_msgs", "gpupager_last_error"]
+           "gpupager_dropped_msgs", "gpupager_last_error",
+           "gpumm_create", "gpumm_process", "gpumm_get_state", "gpumm_destroy"]

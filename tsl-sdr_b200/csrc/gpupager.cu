@@ -1210,3 +1210,136 @@ extern "C" int gpupager_collect_pcm(gpupager_t *h, int16_t *out, size_t cap, siz
 
 extern "C" uint64_t gpupager_kernel_launches(gpupager_t *h) { return h ? h->launches : 0; }
 extern "C" uint64_t gpupager_dropped_msgs(gpupager_t *h) { return h ? h->dropped : 0; }
+
+/* ============================================================================================== */
+/* Mueller-Muller timing recovery (pager/mueller_muller.c:10-115), one thread per channel.           */
+/* ============================================================================================== */
+namespace {
+
+struct MmState { float w, m, next_offset, last_sample; };
+
+__device__ __forceinline__ float mm_sign(float v) { return (float)(v > 0.0f) - (float)(v < 0.0f); }   /* :34-38 */
+
+template <bool FMA>
+__global__ void mm_kernel(MmState *__restrict__ states, int nr_channels, const short *__restrict__ pcm, long long pitch,
+                          unsigned n, float kw, float km, float emin, float emax, short *__restrict__ out, long long cap,
+                          unsigned *__restrict__ nr_out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nr_channels) return;
+    MmState st = states[c];
+    const short *x = pcm + (size_t)c * pitch;
+    short *d = out + (size_t)c * cap;
+    float cur = st.next_offset, w = st.w, m = st.m, last = st.last_sample;
+    const float nf = (float)n;
+    unsigned nd = 0;
+    while (cur < nf && nd < cap) {                                          /* :65 */
+        const float sample = (float)x[(size_t)__fadd_rn(cur, 0.5f)];        /* :66 */
+        d[nd++] = (short)sample;                                            /* :70 */
+        /* :76 -- both products are exact (a sign times an integer-valued float) */
+        const float w_error = __fsub_rn(__fmul_rn(mm_sign(last), sample), __fmul_rn(mm_sign(sample), last));
+        w = FMA ? __fmaf_rn(w_error, kw, w) : __fadd_rn(w, __fmul_rn(w_error, kw));                 /* :79 */
+        if (emin > w) w = emin; else if (emax < w) w = emax;                                        /* :86-90 */
+        m = FMA ? __fadd_rn(m, __fmaf_rn(km, sample, w)) : __fadd_rn(m, __fadd_rn(w, __fmul_rn(km, sample)));   /* :92 */
+        const float fl = floorf(m);
+        cur = __fadd_rn(cur, fl);                                           /* :95 */
+        m = __fsub_rn(m, fl);
+        last = sample;
+    }
+    st.next_offset = __fsub_rn(cur, nf);                                    /* :107-109 */
+    st.w = w; st.m = m; st.last_sample = last;
+    states[c] = st;
+    nr_out[c] = nd;
+}
+
+} // namespace
+
+struct gpumm {
+    int device = 0, C = 0;
+    uint32_t flags = 0;
+    size_t max_feed = 0;
+    float kw = 0, km = 0, emin = 0, emax = 0;
+    cudaStream_t stream = nullptr;
+    MmState *d_states = nullptr;
+    short *d_in = nullptr, *d_out = nullptr;
+    unsigned *d_nr = nullptr;
+};
+
+extern "C" int gpumm_create(gpumm_t **ph, uint32_t nr_channels, int32_t device, float kw, float km, float samples_per_bit,
+                            float error_min, float error_max, uint32_t max_feed_samples, uint32_t flags)
+{
+    if (!ph || !nr_channels || !max_feed_samples) return perr(GPUPAGER_E_BADARGS, "bad argument");
+    *ph = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return perr(GPUPAGER_E_NODEVICE, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return perr(GPUPAGER_E_BADARGS, "bad device ordinal");
+    PCUDA(cudaSetDevice(device));
+    gpumm *h = new (std::nothrow) gpumm();
+    if (!h) return perr(GPUPAGER_E_NOMEM, "out of memory");
+    h->device = device; h->C = (int)nr_channels; h->flags = flags; h->max_feed = max_feed_samples;
+    h->kw = kw; h->km = km; h->emin = error_min; h->emax = error_max;
+    const size_t C = nr_channels;
+    std::vector<MmState> init(C);
+    for (auto &s : init) { s.w = s.m = samples_per_bit; s.next_offset = 0.0f; s.last_sample = 0.0f; }   /* mueller_muller.c:19-20 */
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_states, C * sizeof(MmState));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_states, init.data(), C * sizeof(MmState), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_in, C * h->max_feed * sizeof(short));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_out, C * h->max_feed * sizeof(short));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_nr, C * sizeof(unsigned));
+    if (e != cudaSuccess) {
+        perr(GPUPAGER_E_CUDA, "gpumm_create: %s", cudaGetErrorString(e));
+        gpumm_destroy(&h);
+        return GPUPAGER_E_CUDA;
+    }
+    *ph = h;
+    return GPUPAGER_OK;
+}
+
+extern "C" int gpumm_destroy(gpumm_t **ph)
+{
+    if (!ph || !*ph) return perr(GPUPAGER_E_BADARGS, "null handle");
+    gpumm *h = *ph;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    cudaFree(h->d_states); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_nr);
+    delete h;
+    *ph = nullptr;
+    return GPUPAGER_OK;
+}
+
+extern "C" int gpumm_process(gpumm_t *h, const int16_t *pcm_host, size_t pitch, size_t n, int16_t *decisions_host, size_t cap,
+                             uint32_t *nr_out)
+{
+    if (!h || !pcm_host || !decisions_host || !nr_out) return perr(GPUPAGER_E_BADARGS, "null argument");
+    if (n > h->max_feed) return perr(GPUPAGER_E_INVAL, "feed of %zu samples exceeds max_feed_samples %zu", n, h->max_feed);
+    if (n >= (1u << 24)) return perr(GPUPAGER_E_INVAL, "mm_process counts samples in float: feeds must stay below 2^24 samples");
+    for (int c = 0; c < h->C; c++) nr_out[c] = 0;
+    if (n == 0) return GPUPAGER_OK;
+    PCUDA(cudaSetDevice(h->device));
+    PCUDA(cudaMemcpy2DAsync(h->d_in, h->max_feed * sizeof(short), pcm_host, pitch * sizeof(short), n * sizeof(short), h->C,
+                            cudaMemcpyHostToDevice, h->stream));
+    const long long dcap = (long long)(cap < h->max_feed ? cap : h->max_feed);
+    if (h->flags & GPUMM_F_FMA)
+        mm_kernel<true><<<(h->C + 31) / 32, 32, 0, h->stream>>>(h->d_states, h->C, h->d_in, (long long)h->max_feed, (unsigned)n, h->kw,
+                                                               h->km, h->emin, h->emax, h->d_out, dcap, h->d_nr);
+    else
+        mm_kernel<false><<<(h->C + 31) / 32, 32, 0, h->stream>>>(h->d_states, h->C, h->d_in, (long long)h->max_feed, (unsigned)n, h->kw,
+                                                                h->km, h->emin, h->emax, h->d_out, dcap, h->d_nr);
+    PCUDA(cudaGetLastError());
+    PCUDA(cudaMemcpyAsync(nr_out, h->d_nr, h->C * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+    PCUDA(cudaStreamSynchronize(h->stream));
+    unsigned mx = 0;
+    for (int c = 0; c < h->C; c++) mx = nr_out[c] > mx ? nr_out[c] : mx;
+    if (mx) PCUDA(cudaMemcpy2D(decisions_host, cap * sizeof(short), h->d_out, dcap * sizeof(short), mx * sizeof(short), h->C,
+                               cudaMemcpyDeviceToHost));
+    return GPUPAGER_OK;
+}
+
+extern "C" int gpumm_get_state(gpumm_t *h, uint32_t channel, float state[4])
+{
+    if (!h || !state || channel >= (uint32_t)h->C) return perr(GPUPAGER_E_BADARGS, "bad argument");
+    PCUDA(cudaSetDevice(h->device));
+    PCUDA(cudaMemcpy(state, h->d_states + channel, sizeof(MmState), cudaMemcpyDeviceToHost));
+    return GPUPAGER_OK;
+}

@@ -143,3 +143,39 @@ class GpuPager:
     @property
     def dropped(self):
         return self._L.gpupager_dropped_msgs(self._h)
+
+
+class GpuMM:
+    """ctypes mirror of gpumm_* (Mueller-Muller timing recovery, pager/mueller_muller.c) for nr_channels streams."""
+
+    def __init__(self, nr_channels, kw, km, samples_per_bit, error_min, error_max, max_feed_samples, fma=True, device=0):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self.nr_channels = int(nr_channels)
+        self.max_feed = int(max_feed_samples)
+        _check(self._L.gpumm_create(C.byref(self._h), self.nr_channels, device, kw, km, samples_per_bit, error_min, error_max,
+                                    self.max_feed, 1 if fma else 0), "gpumm_create")
+
+    def process(self, pcm: np.ndarray):
+        """pcm [nr_channels, n] int16 -> list of per-channel decision arrays"""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        n = pcm.shape[1]
+        out = np.zeros((self.nr_channels, max(n, 1)), np.int16)
+        nr = np.zeros(self.nr_channels, np.uint32)
+        _check(self._L.gpumm_process(self._h, pcm.ctypes.data, n, n, out.ctypes.data, out.shape[1], nr.ctypes.data), "gpumm_process")
+        return [out[c, :nr[c]].copy() for c in range(self.nr_channels)]
+
+    def state(self, channel):
+        st = np.zeros(4, np.float32)
+        _check(self._L.gpumm_get_state(self._h, channel, st.ctypes.data), "gpumm_get_state")
+        return st
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.gpumm_destroy(C.byref(self._h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
