@@ -201,6 +201,7 @@ def main():
     import torch
     import tslb200_loader
     tslb200_loader.load_package()
+    from tsl_sdr_b200 import shard
     from tsl_sdr_b200.gpuchan import GpuChan, F_ATAN_FMA
 
     rank = int(os.environ.get("RANK", "0"))
@@ -217,7 +218,9 @@ def main():
 
     n = 1 << args.batch_log2
     lpf, offs_all = channel_plan(world)
-    offs = offs_all[rank * C_PER_GPU:(rank + 1) * C_PER_GPU]
+    ch_lo, ch_hi = shard.shard_range(len(offs_all), world, rank)      # contiguous channel range of this rank
+    offs = offs_all[ch_lo:ch_hi]
+    assert ch_hi - ch_lo == C_PER_GPU
     bank = GpuChan(lpf, offs, FS, D, n, device=local_rank, flags=F_ATAN_FMA, engine=args.engine)
 
     NB = 2
@@ -237,8 +240,7 @@ def main():
 
     def step_resident(i):
         buf = batches[i % NB]
-        if dist is not None:
-            dist.broadcast(buf, src=0)
+        shard.broadcast_iq(dist, buf, src=0)
         bank.submit_device(buf.data_ptr(), n, sptr)
         k = bank.pending()
         bank.discard()                                  # results stay on the device in this leg
@@ -292,7 +294,7 @@ def main():
             buf = batches[i % NB]
             if rank == 0:
                 buf.copy_(pin_in[i % NB], non_blocking=True)
-            dist.broadcast(buf, src=0)
+            shard.broadcast_iq(dist, buf, src=0)
             bank.submit_device(buf.data_ptr(), n, sptr)
 
     def e2e_collect():
