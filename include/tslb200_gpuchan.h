@@ -153,6 +153,14 @@ int gpuchan_tc_selftest(const uint8_t *A0, const uint8_t *B0, const uint8_t *A1,
                         int N, int shift0, int shift1, int a0_signed, int b0_signed, int a1_signed, int b1_signed,
                         int32_t *out);
 
+/* Unit hook for tests: the kernels' re-formulated discriminator arithmetic (csrc/fm_math.cuh "v2") next to literal
+ * transcriptions of multifm/fast_atan2f.c:101-174 and multifm/fm_demod.c:68-72, on the device.
+ *   what = 0: `count` pseudo-random int32 operand pairs (seed) through fast_atan2f and the PCM scaling;
+ *   what = 1: every float bit pattern in [seed_or_first, seed_or_first + count) with |phi| <= 3.2 through the PCM scaling.
+ * out[0] = arctangent results differing in any bit, out[1] = PCM values differing, out[2] = uses of the exact FP64
+ * path, out[3] = offenders recorded, out[4..7] = the first offender's operands and results. */
+int gpuchan_math_selftest(uint32_t what, uint64_t seed_or_first, uint64_t count, uint32_t use_fma, uint64_t out[8]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -487,6 +487,32 @@ static void host_atan_table(float2 *out)
     for (int i = 0; i < 256; i++) out[i] = make_float2(t[i], t[i + 1] - t[i]);
 }
 
+static float host_z_small_thr()
+{
+    /* (double)z < 0.003921569 as a float comparison (fast_atan2f.c:123) */
+    const double res = 0.003921569;
+    float f = (float)res;
+    if ((double)f < res) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+namespace tslb200 {
+cudaError_t run_math_selftest(uint32_t what, uint64_t seed_or_first, uint64_t count, bool use_fma, const float2 *h_tab,
+                              float z_small_thr, uint64_t out[8]);
+}
+
+extern "C" int gpuchan_math_selftest(uint32_t what, uint64_t seed_or_first, uint64_t count, uint32_t use_fma, uint64_t out[8])
+{
+    if (!out || what > 1) return set_err(GPUCHAN_E_BADARGS, "bad selftest arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(GPUCHAN_E_NODEVICE, "no CUDA device: this library has no CPU fallback");
+    float2 tab[256];
+    host_atan_table(tab);
+    CUDA_TRY(tslb200::run_math_selftest(what, seed_or_first, count, use_fma != 0, tab, host_z_small_thr(), out));
+    return GPUCHAN_OK;
+}
+
 static int free_all(gpuchan *h)
 {
     if (!h) return 0;
@@ -663,14 +689,8 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
     FAIL_TRY(cudaMalloc(&h->d_atan, sizeof(tab)));
     FAIL_TRY(cudaMemcpy(h->d_atan, tab, sizeof(tab), cudaMemcpyHostToDevice));
 
-    /* (double)z < 0.003921569 as a float comparison (fast_atan2f.c:123) */
-    {
-        const double res = 0.003921569;
-        float f = (float)res;
-        if ((double)f < res) f = nextafterf(f, INFINITY);
-        h->atan.z_small_thr = f;
-        h->atan.use_fma = (h->flags & GPUCHAN_F_ATAN_FMA) ? 1 : 0;
-    }
+    h->atan.z_small_thr = host_z_small_thr();
+    h->atan.use_fma = (h->flags & GPUCHAN_F_ATAN_FMA) ? 1 : 0;
 
     /* --- derotator limit cycles --- */
     rot_cycle_detect_kernel<<<(C + 63) / 64, 64, 0, h->stream>>>(h->d_incr, C, h->d_mu, h->d_lambda, h->d_cyc);

@@ -1,0 +1,140 @@
+/*
+ * math_selftest.cu -- device-side differential tests of the discriminator arithmetic (test hook of the C ABI).
+ *
+ * The fused kernels use re-formulated ("v2") versions of the reference's scalar helpers (fm_math.cuh).  This
+ * hook runs them next to the literal transcriptions -- fast_atan2f_dev() follows multifm/fast_atan2f.c:101-174
+ * branch for branch, fm_pcm() evaluates multifm/fm_demod.c:68-72 in FP64 -- over pseudo-random operand pairs or
+ * over a whole range of float bit patterns and counts results that differ in any bit.
+ */
+#include "fm_math.cuh"
+
+#include <cstdio>
+
+namespace {
+
+using namespace tslb200;
+
+__device__ __forceinline__ uint64_t splitmix(uint64_t &s)
+{
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+/* operand pairs the discriminator can see: full-range products, small values, equal magnitudes, axes, origin */
+__device__ __forceinline__ void draw_pair(uint64_t &s, int &a, int &b)
+{
+    const uint64_t r = splitmix(s), q = splitmix(s);
+    a = (int)(uint32_t)r;
+    b = (int)(uint32_t)(r >> 32);
+    const unsigned sh_a = (unsigned)(q & 31), sh_b = (unsigned)((q >> 5) & 31), kind = (unsigned)((q >> 10) & 15);
+    a >>= sh_a;
+    b >>= sh_b;
+    if (kind == 0) b = a;
+    else if (kind == 1) b = -a;
+    else if (kind == 2) a = 0;
+    else if (kind == 3) b = 0;
+    else if (kind == 4) { a = 0; b = 0; }
+    else if (kind == 5) b = a + (int)((q >> 16) & 3) - 1;
+    else if (kind == 6) { a = (int)((q >> 16) & 1023) - 512; b = (int)((q >> 32) & 1023) - 512; }
+}
+
+template <bool FMA>
+__global__ void atan_selftest_kernel(uint64_t seed, uint64_t per_thread, const float2 *tab_g, AtanParams ap,
+                                     unsigned long long *out)
+{
+    __shared__ float2 tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = tab_g[i];
+    __syncthreads();
+    const uint32_t tab_smem = (uint32_t)__cvta_generic_to_shared(tab);
+    uint64_t s = seed + 0x1234567ull * (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x);
+    ap.use_fma = FMA ? 1 : 0;
+    unsigned long long bad_atan = 0, bad_pcm = 0, exact = 0;
+    for (uint64_t i = 0; i < per_thread; i++) {
+        int s_im, s_re;
+        draw_pair(s, s_im, s_re);
+        const float ref = fast_atan2f_dev((float)s_im, (float)s_re, tab, ap);
+        const float v2 = fast_atan2f_v2<FMA>(s_im, s_re, tab_smem, ap.z_small_thr);
+        if (__float_as_uint(ref) != __float_as_uint(v2) && !(ref == 0.0f && v2 == 0.0f)) {
+            if (atomicAdd(&out[3], 1ull) == 0) { out[4] = (unsigned)s_im; out[5] = (unsigned)s_re; out[6] = __float_as_uint(ref); out[7] = __float_as_uint(v2); }
+            bad_atan++;
+        }
+        /* the whole discriminator tail: literal FP64 expression vs fast path + guard band + exact fallback */
+        const double q = __dmul_rn(__ddiv_rn((double)ref, 3.14159265358979323846), 16384.0);
+        const int pcm_want = __float2int_rz(__double2float_rn(q));
+        float a, margin = 1.0f;
+        int pcm = pcm_from_phi_v2(v2, a, margin);
+        if (margin < 0.0f) { pcm = pcm_from_phi_exact(a); exact++; }
+        if (pcm != pcm_want) bad_pcm++;
+    }
+    atomicAdd(&out[0], bad_atan);
+    atomicAdd(&out[1], bad_pcm);
+    atomicAdd(&out[2], exact);
+}
+
+/* every float bit pattern in [first, first + count): pcm_from_phi_v2 (+ fallback) against the FP64 expression */
+__global__ void pcm_selftest_kernel(uint32_t first, uint64_t count, unsigned long long *out)
+{
+    unsigned long long bad = 0, exact = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += stride) {
+        const uint32_t bits = first + (uint32_t)i;
+        const float phi = __uint_as_float(bits);
+        if (!(fabsf(phi) <= 3.2f)) continue;            /* the discriminator never leaves [-pi, pi] */
+        const double q = __dmul_rn(__ddiv_rn((double)phi, 3.14159265358979323846), 16384.0);
+        const int pcm_want = __float2int_rz(__double2float_rn(q));
+        float a, margin = 1.0f;
+        int pcm = pcm_from_phi_v2(phi, a, margin);
+        if (margin < 0.0f) { pcm = pcm_from_phi_exact(a); exact++; }
+        if (pcm != pcm_want) {
+            if (atomicAdd(&out[3], 1ull) == 0) { out[4] = bits; out[5] = (unsigned)pcm_want; out[6] = (unsigned)pcm; }
+            bad++;
+        }
+    }
+    atomicAdd(&out[1], bad);
+    atomicAdd(&out[2], exact);
+}
+
+} // namespace
+
+namespace tslb200 {
+
+/* what = 0: `count` pseudo-random operand pairs through the arctangent and the PCM scaling;
+ * what = 1: float bit patterns [seed_or_first, seed_or_first + count) through the PCM scaling.
+ * out[0] arctangent mismatches, out[1] PCM mismatches, out[2] exact-path uses, out[3..7] first offender. */
+cudaError_t run_math_selftest(uint32_t what, uint64_t seed_or_first, uint64_t count, bool use_fma, const float2 *h_tab,
+                              float z_small_thr, uint64_t out[8])
+{
+    unsigned long long *d_out = nullptr;
+    float2 *d_tab = nullptr;
+    cudaError_t e = cudaMalloc(&d_out, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(d_out, 0, 8 * sizeof(unsigned long long));
+    if (what == 0) {
+        if (e == cudaSuccess) e = cudaMalloc(&d_tab, 256 * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMemcpy(d_tab, h_tab, 256 * sizeof(float2), cudaMemcpyHostToDevice);
+        AtanParams ap;
+        ap.z_small_thr = z_small_thr;
+        ap.use_fma = use_fma ? 1 : 0;
+        const unsigned blocks = 592, threads = 256;
+        const uint64_t per_thread = (count + (uint64_t)blocks * threads - 1) / ((uint64_t)blocks * threads);
+        if (e == cudaSuccess) {
+            if (use_fma) atan_selftest_kernel<true><<<blocks, threads>>>(seed_or_first, per_thread, d_tab, ap, d_out);
+            else atan_selftest_kernel<false><<<blocks, threads>>>(seed_or_first, per_thread, d_tab, ap, d_out);
+            e = cudaGetLastError();
+        }
+    } else {
+        if (e == cudaSuccess) {
+            pcm_selftest_kernel<<<1184, 256>>>((uint32_t)seed_or_first, count, d_out);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    cudaFree(d_tab);
+    return e;
+}
+
+} // namespace tslb200

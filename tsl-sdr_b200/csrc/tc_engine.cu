@@ -35,6 +35,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 namespace tslb200 {
 
@@ -256,24 +257,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
     } else {
         /* ================= epilogue: TMEM -> registers -> derotate -> discriminate -> PCM =================
          * Accumulator row 32*s + i (i < 16) is the real part of channel 16*s + i, row 32*s + 16 + i its imaginary
-         * part, so lanes i and i + 16 of the warp that owns TMEM lane slice s hold the two halves of one channel.
-         * Warp (s, pair) drains columns TC_LEAD + 16*pair + [-1, 16): lane i keeps the first 8 columns, lane i + 16
-         * the last 8, and one shuffle per column hands each its missing half. */
+         * part.  Warp (s, pair) drains columns TC_LEAD + 16*pair + [-1, 16) with the 16x32bx2 load shape: lanes
+         * 0-15 receive the first 8 columns and lanes 16-31 the last 8 columns of the SAME 16 TMEM lanes, once for the
+         * real rows and once for the imaginary rows, so every thread ends up with both components of its own
+         * channel x 8 outputs -- no shuffles, no selects.
+         * The arithmetic (fm_math.cuh "v2") is arranged for the pipe split of sm_100: ncu showed the previous
+         * epilogue bound by the ALU pipe (67 % busy, FMA pipe 24 %), so selects/compares became multiply-adds. */
         const int e = warp - EPI_WARP0;
         const int slice = warp & 3;
         const int pair = e >> 2;
         const bool hi = lane >= 16;
         const int ch = 16 * slice + (lane & 15);
         const int blk = 2 * pair + (hi ? 1 : 0);    /* which 8-output block of the tile this thread turns into PCM */
-        const uint32_t lane_base = (uint32_t)(32 * slice) << 16;
+        const uint32_t lane_re = (uint32_t)(32 * slice) << 16, lane_im = (uint32_t)(32 * slice + 16) << 16;
         const int c = g * TC_CH + ch;
         const bool live = c < p.C;
         const int iw = live ? __ldg(p.incr + c) : 0;
-        const int i_re = lo16(iw), i_im = hi16(iw);
+        const int i4_re = 4 * lo16(iw), i4_im = 4 * hi16(iw);
         short *const pcm_c = p.pcm + (size_t)c * p.pitch;
         int *const iq_c = KEEP_IQ ? p.iq_out + (size_t)c * p.pitch : nullptr;
-        AtanParams ap = p.atan;
-        ap.use_fma = FMA ? 1 : 0;
+        const float z_thr = p.atan.z_small_thr;
+        const uint32_t atan_smem = ptx::smem_u32(atan_s);
         /* Steady state (every channel on its limit cycle): the phase of the output before my first one comes from the
          * channel's cycle table; it advances by TC_OUT outputs per tile. */
         const bool table_mode = p.ckpt == nullptr;
@@ -286,112 +290,126 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             tstep = (uint32_t)TC_OUT % lam;
             tab = p.cyc + (size_t)c * p.cyc_pitch;
         }
+        /* derotator phase word of tile `it` of this CTA: the phase of the output before my block (of output 0 itself
+         * for the very first block of the stream segment); fetched one tile ahead so that its latency hides behind
+         * the arithmetic of the current tile */
+        auto phase_word = [&](int it) -> int {
+            if (!live) return 0;
+            const int tile = tile0 + it;
+            if (table_mode) {
+                uint32_t ix = tph;
+                if (tile == 0 && blk == 0) { ix++; if (ix == lam) ix = 0; }
+                tph += tstep;
+                if (tph >= lam) tph -= lam;
+                return __ldg(tab + ix);
+            }
+            return __ldg(p.ckpt + ((size_t)tile * TC_SUB + blk) * p.C + c);
+        };
+        int cwk_next = my_tiles > 0 ? phase_word(0) : 0;
 
         int st = 0, pht = 0;
         for (int it = 0; it < my_tiles; it++) {
             const int tile = tile0 + it;
+            const int cwk = cwk_next;
             if (tid == 0) DBG(2, it, 0);
-            ptx::mbar_wait_backoff(&t_full[st], pht, 64);
+            ptx::mbar_wait_backoff(&t_full[st], pht, 32);
             if (tid == 0) DBG(2, it, 1);
             ptx::tc_fence_after();
-            /* ---- drain: 16 columns + the one before them, every limb accumulator; recombine modulo 2^32 ---- */
-            int v[16], vl;
+            /* ---- drain my 8 columns + the one before them, both components, every limb accumulator ---- */
+            int x_re[8], x_im[8], xl_re, xl_im;     /* 4 * acc + 0x8000 (mod 2^32): top 16 bits = rq14(acc) */
             {
-                const uint32_t col0 = tmem_base + (uint32_t)st * STAGE_COLS + lane_base + TC_LEAD + 16 * pair;
-                int a0[16], a1[16], a2[16], l0, l1, l2 = 0;
-                ptx::tmem_ld16(col0, a0);
-                ptx::tmem_ld16(col0 + TC_ACC_STRIDE, a1);
-                if (ACCS == 3) ptx::tmem_ld16(col0 + 2 * TC_ACC_STRIDE, a2);
-                ptx::tmem_ld1(col0 - 1, l0);
-                ptx::tmem_ld1(col0 - 1 + TC_ACC_STRIDE, l1);
-                if (ACCS == 3) ptx::tmem_ld1(col0 - 1 + 2 * TC_ACC_STRIDE, l2);
-                ptx::tmem_ld_wait();
+                const uint32_t col0 = tmem_base + (uint32_t)st * STAGE_COLS + TC_LEAD + 16 * pair;
+                int a0r[8], a1r[8], a2r[8], a0i[8], a1i[8], a2i[8], l0r, l1r, l2r = 0, l0i, l1i, l2i = 0;
+                ptx::tmem_ld8_split8(col0 + lane_re, a0r);
+                ptx::tmem_ld8_split8(col0 + lane_im, a0i);
+                ptx::tmem_ld8_split8(col0 + lane_re + TC_ACC_STRIDE, a1r);
+                ptx::tmem_ld8_split8(col0 + lane_im + TC_ACC_STRIDE, a1i);
                 if (ACCS == 3) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = a2[i] + (a1[i] << 8) + (a0[i] << 16);
-                    vl = l2 + (l1 << 8) + (l0 << 16);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = a1[i] + (a0[i] << 8);
-                    vl = l1 + (l0 << 8);
+                    ptx::tmem_ld8_split8(col0 + lane_re + 2 * TC_ACC_STRIDE, a2r);
+                    ptx::tmem_ld8_split8(col0 + lane_im + 2 * TC_ACC_STRIDE, a2i);
                 }
+                ptx::tmem_ld1_split8(col0 - 1 + lane_re, l0r);
+                ptx::tmem_ld1_split8(col0 - 1 + lane_im, l0i);
+                ptx::tmem_ld1_split8(col0 - 1 + lane_re + TC_ACC_STRIDE, l1r);
+                ptx::tmem_ld1_split8(col0 - 1 + lane_im + TC_ACC_STRIDE, l1i);
+                if (ACCS == 3) {
+                    ptx::tmem_ld1_split8(col0 - 1 + lane_re + 2 * TC_ACC_STRIDE, l2r);
+                    ptx::tmem_ld1_split8(col0 - 1 + lane_im + 2 * TC_ACC_STRIDE, l2i);
+                }
+                ptx::tmem_ld_wait();
+                /* limb weights: SUM (2^8, 1), RADIX (2^16, 2^8, 1); times 4 and + 0x8000 for the rounding shift */
+                auto comb = [](int a0, int a1, int a2) -> int {
+                    if (ACCS == 3) return (int)((unsigned)a2 * 4u + ((unsigned)a1 * 1024u + ((unsigned)a0 * 262144u + 0x8000u)));
+                    return (int)((unsigned)a1 * 4u + ((unsigned)a0 * 1024u + 0x8000u));
+                };
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    x_re[u] = comb(a0r[u], a1r[u], ACCS == 3 ? a2r[u] : 0);
+                    x_im[u] = comb(a0i[u], a1i[u], ACCS == 3 ? a2i[u] : 0);
+                }
+                xl_re = comb(l0r, l1r, l2r);
+                xl_im = comb(l0i, l1i, l2i);
             }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&t_empty[st]);  /* TMEM stage is free again */
             if (tid == 0) DBG(2, it, 2);
             if (++st == NT) { st = 0; pht ^= 1; }
-
-            /* ---- pair up re / im: mine = the component my row holds, other = the partner's ---- */
-            int mine[8], other[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                mine[u] = hi ? v[8 + u] : v[u];
-                other[u] = __shfl_xor_sync(0xffffffffu, hi ? v[u] : v[8 + u], 16);
-            }
-            const int lead_mine = hi ? v[7] : vl;
-            const int lead_other = __shfl_xor_sync(0xffffffffu, hi ? vl : v[7], 16);
+            if (it + 1 < my_tiles) cwk_next = phase_word(it + 1);
 
             /* ---- one channel x 8 consecutive outputs per thread ---- */
             const long long kfirst = (long long)TC_OUT * tile + 8 * blk;        /* output index of this thread's first column */
             const int nvalid = (p.K - kfirst > 8) ? 8 : (int)(p.K - kfirst);
             if (live && nvalid > 0 && !(p.dbg_flags & 1)) {
-                int cwk;
-                if (table_mode) {
-                    uint32_t ix = tph;
-                    if (kfirst == 0) { ix++; if (ix == lam) ix = 0; }      /* phase of output 0 itself */
-                    cwk = __ldg(tab + ix);
-                } else {
-                    cwk = __ldg(p.ckpt + ((size_t)tile * TC_SUB + blk) * p.C + c);
-                }
                 int r_re = lo16(cwk), r_im = hi16(cwk);
                 int p_re, p_im;
                 if (kfirst == 0) {
-                    /* very first output of the submit: y[-1] is carried state; checkpoint = phase of output 0 */
+                    /* very first output of the submit: y[-1] is carried state; the phase word = phase of output 0 */
                     const int lw = __ldg(p.last_in + c);
                     p_re = lo16(lw); p_im = hi16(lw);
                 } else {
-                    /* previous output = the column before my block; the checkpoint is its phase */
-                    const int l_re = hi ? lead_other : lead_mine, l_im = hi ? lead_mine : lead_other;
-                    derotate(rq14(l_re), rq14(l_im), r_re, r_im, p_re, p_im);
-                    rot_step(r_re, r_im, i_re, i_im);
+                    /* previous output = the column before my block; the phase word is its phase */
+                    derotate_v2(xl_re >> 16, xl_im >> 16, r_re, r_im, p_re, p_im);
+                    rot_step_v2(r_re, r_im, i4_re, i4_im);
                 }
-                int pcm[8], l_re = 0, l_im = 0;
-                float av[8];
-                uint32_t exact_mask = 0;
+                /* EDGE = this block holds the submit's last output (or is cut short by it): also track y[K-1] */
+                auto block8 = [&](auto edge_tag) {
+                    constexpr bool EDGE = decltype(edge_tag)::value;
+                    int pcm[8], l_re = 0, l_im = 0;
+                    float av[8];
+                    float margin = 1.0f;
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int q_re = hi ? other[u] : mine[u], q_im = hi ? mine[u] : other[u];
-                    int y_re, y_im;
-                    derotate(rq14(q_re), rq14(q_im), r_re, r_im, y_re, y_im);
-                    rot_step(r_re, r_im, i_re, i_im);
-                    bool ex;
-                    pcm[u] = pcm_from_phi_fast(fm_phi_bf(y_re, y_im, p_re, p_im, atan_s, ap), av[u], ex);
-                    exact_mask |= (ex ? 1u : 0u) << u;
-                    if (KEEP_IQ) { if (u < nvalid) iq_c[kfirst + u] = pack16(y_re, y_im); }
-                    p_re = y_re; p_im = y_im;
-                    if (u == nvalid - 1) { l_re = y_re; l_im = y_im; }
-                }
-                if (exact_mask) {       /* about 1 output in 60000: redo it in FP64 */
+                    for (int u = 0; u < 8; u++) {
+                        int y_re, y_im;
+                        derotate_v2(x_re[u] >> 16, x_im[u] >> 16, r_re, r_im, y_re, y_im);
+                        rot_step_v2(r_re, r_im, i4_re, i4_im);
+                        const int s_re = (int)((unsigned)y_re * (unsigned)p_re + (unsigned)y_im * (unsigned)p_im);    /* y * conj(prev) */
+                        const int s_im = (int)((unsigned)y_im * (unsigned)p_re - (unsigned)y_re * (unsigned)p_im);
+                        pcm[u] = pcm_from_phi_v2(fast_atan2f_v2<FMA>(s_im, s_re, atan_smem, z_thr), av[u], margin);
+                        if (KEEP_IQ) { if (!EDGE || u < nvalid) iq_c[kfirst + u] = pack16(y_re, y_im); }
+                        p_re = y_re; p_im = y_im;
+                        if (EDGE) { if (u == nvalid - 1) { l_re = y_re; l_im = y_im; } }
+                    }
+                    if (margin < 0.0f) {    /* about 1 block in 4000: some output sits on a float rounding boundary -> FP64 */
 #pragma unroll
-                    for (int u = 0; u < 8; u++)
-                        if (exact_mask & (1u << u)) pcm[u] = pcm_from_phi_exact(av[u]);
-                }
-                uint32_t out[4];
+                        for (int u = 0; u < 8; u++) pcm[u] = pcm_from_phi_exact(av[u]);
+                    }
+                    uint32_t out[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) out[u] = ((uint32_t)pcm[2 * u] & 0xffffu) | ((uint32_t)pcm[2 * u + 1] << 16);
-                if (nvalid == 8) {
-                    *reinterpret_cast<uint4 *>(pcm_c + kfirst) = make_uint4(out[0], out[1], out[2], out[3]);
-                } else {
+                    for (int u = 0; u < 4; u++) out[u] = ((uint32_t)pcm[2 * u] & 0xffffu) | ((uint32_t)pcm[2 * u + 1] << 16);
+                    if (!EDGE || nvalid == 8) {
+                        *reinterpret_cast<uint4 *>(pcm_c + kfirst) = make_uint4(out[0], out[1], out[2], out[3]);
+                    } else {
 #pragma unroll
-                    for (int u = 0; u < 8; u++)
-                        if (u < nvalid) pcm_c[kfirst + u] = (short)(out[u >> 1] >> (16 * (u & 1)));
-                }
-                /* the thread that produced the submit's last output hands y[K-1] to the next submit */
-                if (kfirst + nvalid == p.K) p.last_out[c] = pack16(l_re, l_im);
+                        for (int u = 0; u < 8; u++)
+                            if (u < nvalid) pcm_c[kfirst + u] = (short)(out[u >> 1] >> (16 * (u & 1)));
+                    }
+                    /* the thread that produced the submit's last output hands y[K-1] to the next submit */
+                    if (EDGE) { if (kfirst + nvalid == p.K) p.last_out[c] = pack16(l_re, l_im); }
+                };
+                if (kfirst + 8 < p.K) block8(std::false_type{});
+                else block8(std::true_type{});
             }
-            tph += tstep;
-            if (tph >= lam) tph -= lam;
             if (tid == 0) DBG(2, it, 4);
         }
     }

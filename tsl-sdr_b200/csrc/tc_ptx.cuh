@@ -147,6 +147,21 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, int &v)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
+/* TMEM -> registers, shape 16x32bx2 with a half-split offset of 8 columns: threads 0-15 of the warp receive
+ * columns [c, c + 8) of TMEM lanes L .. L + 15, threads 16-31 columns [c + 8, c + 16) of the SAME 16 lanes
+ * (L = lane field of taddr: the warp's 32-lane slice, optionally + 16).  Measured with tools/tmem_probe.cu.
+ * This hands every thread the 8 columns it owns without any shuffle or select. */
+__device__ __forceinline__ void tmem_ld8_split8(uint32_t taddr, int (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], 8;"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+/* one column per thread: column c for threads 0-15, column c + 8 for threads 16-31 */
+__device__ __forceinline__ void tmem_ld1_split8(uint32_t taddr, int &v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x1.b32 {%0}, [%1], 8;" : "=r"(v) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 } // namespace ptx
