@@ -471,6 +471,7 @@ struct gpuchan {
     long long plane_rows = 0;
     long long *d_dbg = nullptr;             /* role clock stamps (GPUCHAN_DEBUG_STAMPS=1) */
     int nr_sms = 148;
+    int tc_tune = 0;                        /* GPUCHAN_TC_TUNE: kernel experiment switches (tc_engine.cu) */
 };
 
 static void host_atan_table(float2 *out)
@@ -652,6 +653,7 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
             FAIL_TRY(cudaEventCreateWithFlags(&h->ev_pre_done[i], cudaEventDisableTiming));
             FAIL_TRY(cudaEventCreateWithFlags(&h->ev_main_done[i], cudaEventDisableTiming));
         }
+        if (getenv("GPUCHAN_TC_TUNE")) h->tc_tune = atoi(getenv("GPUCHAN_TC_TUNE"));
         if (getenv("GPUCHAN_DEBUG_STAMPS")) {
             FAIL_TRY(cudaMalloc(&h->d_dbg, 3 * 32 * 8 * sizeof(long long)));
             FAIL_TRY(cudaMemset(h->d_dbg, 0, 3 * 32 * 8 * sizeof(long long)));
@@ -848,6 +850,7 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
             tb.K = K; tb.geom = tg; tb.atan = h->atan;
             tb.dbg = h->d_dbg;
             tb.dbg_flags = (h->d_dbg && getenv("GPUCHAN_DEBUG_SKIP")) ? atoi(getenv("GPUCHAN_DEBUG_SKIP")) : 0;
+            tb.tune = h->tc_tune;
             CUDA_TRY(tc_launch_fir_fm(h->tc, tb, st));
             h->launches++;
         } else {

@@ -18,15 +18,17 @@
  *   RADIX (any int16 taps): v = 256*hi + lo, four products per K chunk into three accumulators (2^16, 2^8, 1).
  * Only the K chunks a block-row really covers are issued (the last block-row of the filter is usually short).
  *
- * Kernel tc_fir_fm_kernel: persistent, warp specialised (25 warps):
- *   warps 0-15  epilogue: drain TMEM (LDTM) straight into registers, recombine the limbs, pair re/im rows with one
- *               warp shuffle, and run the exact rq / derotator recurrence / discriminator (fm_math.cuh); every thread
- *               owns 8 consecutive outputs of one channel = one 16-byte PCM store.  No shared-memory staging and no
- *               CTA-wide barriers: a tile's 16 lead-in columns make it self-contained.
+ * Kernel tc_fir_fm_kernel: persistent, warp specialised (26 warps):
+ *   warps 0-15  epilogue: drain TMEM (LDTM, shape 16x32bx2: both components of a thread's own 8 columns) straight
+ *               into registers, recombine the limbs, and run the exact rq / derotator recurrence / discriminator
+ *               (fm_math.cuh); every thread owns 8 consecutive outputs of one channel = one 16-byte PCM store.  No
+ *               shared-memory staging, no shuffles and no CTA-wide barriers: a tile's 16 lead-in columns make it
+ *               self-contained.
  *   warps 16-23 transform: read the raw cs16 tile from HBM/L2 and split it into two byte planes (hi s8 / lo u8) in
  *               "slab" order [16-byte K slab][block-row][16 B] (rows zero padded to Kp = round_up(2D, 32) bytes)
  *               directly in an NB-stage shared-memory ring;
- *   warp  24    issues the tile's MMA program (tcgen05.mma kind::i8, SASS UTCIMMA) into an NT-stage TMEM ring.
+ *   warps 24-25 issue the tile's MMA program (tcgen05.mma kind::i8, SASS UTCIMMA) into an NT-stage TMEM ring, each
+ *               warp the MMAs of its own limb accumulators.
  * The B operand needs no im2col: with K-major / no-swizzle descriptors the Q row shifts are just +16 B on the
  * operand start address (validated by tc_selftest.cu).
  */
@@ -47,8 +49,9 @@ constexpr int XF_THREADS = 32 * XF_WARPS;
 /* Warp roles, lowest warp index first: epilogue | transform | MMA issuer. */
 constexpr int EPI_WARP0 = 0;            /* must be a multiple of 4: warp w may only read TMEM lanes 32*(w%4).. */
 constexpr int XF_WARP0 = EPI_WARPS;     /* first transform warp */
-constexpr int MMA_WARP = EPI_WARPS + XF_WARPS;      /* warp index of the MMA issuer */
-constexpr int TC_THREADS = 32 * (XF_WARPS + 1 + EPI_WARPS);
+constexpr int MMA_WARPS = 2;            /* MMA issuers: each owns a disjoint set of limb accumulators */
+constexpr int MMA_WARP = EPI_WARPS + XF_WARPS;      /* warp index of the first MMA issuer */
+constexpr int TC_THREADS = 32 * (XF_WARPS + MMA_WARPS + EPI_WARPS);
 constexpr int NB_MAX = 4, NT_MAX = 3;
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -73,12 +76,14 @@ struct TcKernelParams {
     int n_tiles;            /* tiles per CTA */
     int total_tiles;
     int C, G, Kp, Q, R;
-    int nb_stages, prog_len;
+    int nb_stages, prog_len, prog_split;
     float inv_nslab;
     uint32_t a_group_bytes, b_stage_bytes;
     AtanParams atan;
     long long *dbg;         /* optional per-role clock stamps of CTA 0 (bench diagnostics) */
     int dbg_flags;          /* diagnostics only: 1 = skip the epilogue arithmetic, 2 = skip the transform */
+    int tune;               /* experiments (GPUCHAN_TC_TUNE): 1 = epilogue polls t_full with nanosleep instead of a suspended
+                               try_wait, 2 = same for the transform's b_empty wait, 4 = generic (select-based) transform loads */
     TcMma prog[TC_PROG_MAX];
 };
 
@@ -147,8 +152,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         for (int i = tid; i < 256; i += TC_THREADS) atan_s[i] = p.atan_tab[i];
     }
     if (tid == 0) {
-        for (int s = 0; s < NB_MAX; s++) { ptx::mbar_init(&b_full[s], XF_WARPS); ptx::mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < NT_MAX; s++) { ptx::mbar_init(&t_full[s], 1); ptx::mbar_init(&t_empty[s], EPI_WARPS); }
+        for (int s = 0; s < NB_MAX; s++) { ptx::mbar_init(&b_full[s], XF_WARPS); ptx::mbar_init(&b_empty[s], MMA_WARPS); }
+        for (int s = 0; s < NT_MAX; s++) { ptx::mbar_init(&t_full[s], MMA_WARPS); ptx::mbar_init(&t_empty[s], EPI_WARPS); }
         ptx::fence_mbar_init();
     }
     if (warp_u == MMA_WARP) ptx::tmem_alloc(&tmem_base_s, 512);
@@ -184,7 +189,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         int s = 0, ph = 0;
         for (int it = 0; it < my_tiles; it++) {
             if (xt == 0) { DBG(0, it, 0); prefetch_tile(tile0 + it + 3); }
-            ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, 256);
+            if (p.tune & 2) ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, 256);
+            else ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1, 100000);
             if (xt == 0) DBG(0, it, 1);
             uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
             const long long row_base = (long long)TC_OUT * (tile0 + it) - TC_LEAD;
@@ -193,13 +199,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             if (p.dbg_flags & 2) {
             } else if (s_first >= p.in.carry_len + 4 && s_last <= p.in.total) {
                 const int *base = p.in.fresh + (s_first - p.in.carry_len);
+                const uint32_t o_tile = (uint32_t)(reinterpret_cast<uintptr_t>(base) >> 2) & 3u;
+                if ((p.D & 3) == 0 && !(p.tune & 4)) {
+                    /* rows start a multiple of 4 samples apart: every 8-sample item of the tile has the same
+                     * misalignment o_tile against 16 bytes, so the word rotation is resolved at compile time */
+                    const uint4 *abase = reinterpret_cast<const uint4 *>(reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)15);
+                    auto run = [&](auto o_tag) {
+                        constexpr int O = decltype(o_tag)::value;
 #pragma unroll 4
-                for (int item = xt; item < items; item += XF_THREADS) {
-                    const int m = __float2int_rz(__fmul_rn((float)item + 0.5f, p.inv_nslab));
-                    const int j = item - m * nslab;
-                    uint32_t w[8];
-                    load8_unaligned(base + m * p.D + 8 * j, w);
-                    split_store(w, dst + (size_t)j * slab_bytes + m * 16, dst + (size_t)(nslab + j) * slab_bytes + m * 16);
+                        for (int item = xt; item < items; item += XF_THREADS) {
+                            const int m = __float2int_rz(__fmul_rn((float)item + 0.5f, p.inv_nslab));
+                            const int j = item - m * nslab;
+                            const uint4 *al = abase + ((m * p.D) >> 2) + 2 * j;
+                            const uint4 v0 = __ldg(al), v1 = __ldg(al + 1);
+                            uint4 v2 = make_uint4(0, 0, 0, 0);
+                            if (O) v2 = __ldg(al + 2);
+                            const uint32_t c[12] = { v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w };
+                            uint32_t w[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) w[u] = c[O + u];
+                            split_store(w, dst + (size_t)j * slab_bytes + m * 16, dst + (size_t)(nslab + j) * slab_bytes + m * 16);
+                        }
+                    };
+                    if (o_tile == 0) run(std::integral_constant<int, 0>{});
+                    else if (o_tile == 1) run(std::integral_constant<int, 1>{});
+                    else if (o_tile == 2) run(std::integral_constant<int, 2>{});
+                    else run(std::integral_constant<int, 3>{});
+                } else {
+#pragma unroll 4
+                    for (int item = xt; item < items; item += XF_THREADS) {
+                        const int m = __float2int_rz(__fmul_rn((float)item + 0.5f, p.inv_nslab));
+                        const int j = item - m * nslab;
+                        uint32_t w[8];
+                        load8_unaligned(base + m * p.D + 8 * j, w);
+                        split_store(w, dst + (size_t)j * slab_bytes + m * 16, dst + (size_t)(nslab + j) * slab_bytes + m * 16);
+                    }
                 }
             } else {
                 for (int item = xt; item < items; item += XF_THREADS) {
@@ -220,13 +254,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         /* keep the tail of the window the next submit still needs (fewer than T samples) */
         if (blockIdx.x == 0 && p.carry_out)
             for (int i = xt; i < p.carry_keep; i += XF_THREADS) p.carry_out[i] = in_sample(p.in, p.carry_from + i);
-    } else if (warp_u == MMA_WARP) {
-        /* ================= MMA issuer =================
-         * The whole warp walks the (warp-uniform) loops so that descriptors live in uniform registers; only the
-         * tcgen05 instructions themselves are issued by one lane. */
-        const bool leader = lane == 0;
-        const uint64_t descA0 = ptx::smem_desc_kmajor_noswz(ptx::smem_u32(sA), 2048, 128);
-        const uint64_t descB0 = ptx::smem_desc_kmajor_noswz(ptx::smem_u32(sB), (uint32_t)p.R * 16, 128);
+    } else if (warp_u >= MMA_WARP) {
+        /* ================= MMA issuers =================
+         * Two warps, each issuing the MMAs of its own accumulators (SUM: the 2^8 / the 2^0 limb; RADIX: limbs
+         * {2^16, 2^0} / {2^8}), so no ordering is needed between them; both commit to the same barriers.  The whole
+         * warp walks the (warp-uniform) loop so that descriptors live in uniform registers; only the tcgen05
+         * instructions themselves are issued by one lane. */
+        const int mw = warp_u - MMA_WARP;
+        const bool leader = lane == 0 && mw == 0;
+        const int i0 = mw == 0 ? 0 : p.prog_split, i1 = mw == 0 ? p.prog_split : p.prog_len;
+        const uint32_t a_base = ptx::smem_u32(sA) >> 4, b_base0 = ptx::smem_u32(sB) >> 4;
+        constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);      /* SBO = 128 B, descriptor version 1 (bit 46) */
         int sb = 0, phb = 0, st = 0, pht = 0;
         for (int it = 0; it < my_tiles; it++) {
             if (leader) DBG(1, it, 0);
@@ -236,14 +274,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             if (leader) DBG(1, it, 2);
             ptx::tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)st * STAGE_COLS;
-            const uint64_t dB = descB0 + (uint64_t)(((uint32_t)sb * p.b_stage_bytes) >> 4);
+            const uint32_t b_base = b_base0 + (((uint32_t)sb * p.b_stage_bytes) >> 4);
 #pragma unroll 4
-            for (int i = 0; i < p.prog_len; i++) {
+            for (int i = i0; i < i1; i++) {
                 const TcMma m = p.prog[i];
-                const uint64_t da = descA0 + (uint64_t)(m.w0 & 0x3fffu);
-                const uint64_t db = dB + (uint64_t)((m.w0 >> 14) & 0x1fffu);
-                const uint32_t d = acc + ((m.w0 >> 28) & 3u) * TC_ACC_STRIDE;
-                if (ptx::elect_one()) ptx::mma_i8(d, da, db, m.w1, (m.w0 >> 27) & 1u);
+                const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.a_lo + a_base);
+                const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.b_lo + b_base);
+                const uint32_t d = acc + (m.d_acc & 0xffffu);
+                if (ptx::elect_one()) ptx::mma_i8(d, da, db, m.idesc, m.d_acc >> 31);
             }
             if (ptx::elect_one()) {
                 ptx::mma_commit(&b_empty[sb]);      /* smem stage may be refilled once these MMAs have read it */
@@ -312,7 +350,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             const int tile = tile0 + it;
             const int cwk = cwk_next;
             if (tid == 0) DBG(2, it, 0);
-            ptx::mbar_wait_backoff(&t_full[st], pht, 32);
+            if (p.tune & 1) ptx::mbar_wait_backoff(&t_full[st], pht, 32);
+            else ptx::mbar_wait_sleep(&t_full[st], pht, 100000);
             if (tid == 0) DBG(2, it, 1);
             ptx::tc_fence_after();
             /* ---- drain my 8 columns + the one before them, both components, every limb accumulator ---- */
@@ -484,14 +523,17 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
     const uint32_t plane_lo16 = nslab * slab16;
     if ((size_t)2 * nslab * slab16 >= 8192) { pl.why = "sample tile too large for the MMA program encoding"; return pl; }
     std::vector<bool> started(pl.accs, false);
+    std::vector<TcMma> part[2];         /* per issuing warp; acc 0 and 2 -> warp 0, acc 1 -> warp 1 */
     auto emit = [&](int chunk_idx, bool b_lo, int q, int kk, int acc, int idesc) {
         TcMma m;
         const uint32_t a_off16 = (uint32_t)chunk_idx * 256;
         const uint32_t b_off16 = (b_lo ? plane_lo16 : 0) + (uint32_t)kk * 2 * slab16 + (uint32_t)q;
-        m.w0 = a_off16 | (b_off16 << 14) | ((started[acc] ? 1u : 0u) << 27) | ((uint32_t)acc << 28);
-        m.w1 = ptx::idesc_i8(128, TC_N, !(idesc & 2), !(idesc & 1));
+        m.a_lo = a_off16 | ((2048u >> 4) << 16);                    /* LBO of the tap image: 2048 B between the K halves */
+        m.b_lo = b_off16 | ((uint32_t)pl.R << 16);                  /* LBO of a sample stage: R * 16 B */
+        m.d_acc = (uint32_t)acc * TC_ACC_STRIDE | ((started[acc] ? 1u : 0u) << 31);
+        m.idesc = ptx::idesc_i8(128, TC_N, !(idesc & 2), !(idesc & 1));
         started[acc] = true;
-        pl.prog.push_back(m);
+        part[acc & 1].push_back(m);
     };
     if (pl.mode == TC_MODE_SUM) {
         /* term 0 everywhere, further terms where an entry exceeds 127 * term; acc 0 = weight 2^8 (x hi, signed),
@@ -518,6 +560,9 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
         }
     }
     pl.a_chunks = (int)pl.chunks.size();
+    pl.prog = part[0];
+    pl.prog_split = (int)part[0].size();
+    pl.prog.insert(pl.prog.end(), part[1].begin(), part[1].end());
     if (pl.prog.size() > (size_t)TC_PROG_MAX) { pl.why = "too many MMAs per tile (taps / decimation too large)"; return pl; }
     if (pl.a_chunks * 256 >= 16384) { pl.why = "tap image too large for the MMA program encoding"; return pl; }
     pl.a_group_bytes = (size_t)pl.a_chunks * 4096;
@@ -603,12 +648,13 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     p.atan_tab = b.atan_tab; p.pcm = b.pcm; p.iq_out = b.iq_out; p.pitch = b.pitch; p.K = (long long)b.K;
     p.n_tiles = b.geom.n_tiles; p.total_tiles = b.geom.total_tiles;
     p.C = pl.C; p.G = pl.G; p.Kp = pl.Kp; p.Q = pl.Q; p.R = pl.R;
-    p.nb_stages = pl.nb_stages; p.prog_len = (int)pl.prog.size();
+    p.nb_stages = pl.nb_stages; p.prog_len = (int)pl.prog.size(); p.prog_split = pl.prog_split;
     p.inv_nslab = 1.0f / (float)(pl.Kp / 16);
     p.a_group_bytes = (uint32_t)pl.a_group_bytes; p.b_stage_bytes = (uint32_t)pl.b_stage_bytes;
     p.atan = b.atan;
     p.dbg = b.dbg;
     p.dbg_flags = b.dbg_flags;
+    p.tune = b.tune;
     memcpy(p.prog, pl.prog.data(), pl.prog.size() * sizeof(TcMma));
     /* persistent grid: one CTA per (tile range, channel group), at most one per SM */
     const unsigned ctas = (unsigned)b.geom.chunks * (unsigned)pl.G;

@@ -20,13 +20,15 @@ constexpr int TC_PROG_MAX = 160;        /* MMA instructions per tile the kernel 
 
 enum { TC_MODE_SUM = 0, TC_MODE_RADIX = 1 };
 
-/* One tcgen05.mma of the per-tile program, packed for cheap decoding on the uniform datapath:
- *   w0 = a_off16 (bits 0-13: tap-image offset of the 128 x 32 B chunk, in 16-byte units)
- *      | b_off16 (bits 14-26: sample-stage offset of the (plane, K chunk, row shift), in 16-byte units)
- *      | accumulate (bit 27: 0 for the first MMA into an accumulator) | accumulator index (bits 28-29)
- *   w1 = the kind::i8 instruction descriptor (operand signedness, M, N) */
+/* One tcgen05.mma of the per-tile program, pre-digested on the host so that the issuing warp needs one 16-byte
+ * constant load and two adds per instruction (the uniform datapath that feeds UTCIMMA is slow):
+ *   a_lo  = low word of the A (tap image) shared-memory descriptor without the image base: chunk offset in 16-byte
+ *           units | LBO << 16;  the kernel adds smem_addr(image) >> 4
+ *   b_lo  = same for the B (sample stage) operand: (plane, K chunk, row shift) offset | LBO << 16;  + stage base
+ *   d_acc = TMEM column offset of the accumulator inside a stage | accumulate << 31 (0 for the first MMA into it)
+ *   idesc = the kind::i8 instruction descriptor (operand signedness, M, N) */
 struct TcMma {
-    uint32_t w0, w1;
+    uint32_t a_lo, b_lo, d_acc, idesc;
 };
 
 struct TcPlan {
@@ -45,7 +47,8 @@ struct TcPlan {
     size_t a_group_bytes = 0;           /* bytes of one group's tap image */
     size_t b_stage_bytes = 0;           /* bytes of one sample tile (both planes) */
     size_t smem_bytes = 0;
-    std::vector<TcMma> prog;            /* the MMAs of one tile, in issue order */
+    std::vector<TcMma> prog;            /* the MMAs of one tile: [0, prog_split) issued by MMA warp 0, the rest by warp 1 */
+    int prog_split = 0;                 /* the two warps own disjoint accumulators, so their order does not matter */
     /* tap image construction: for image chunk i, which (q, kk) it covers and which limb/term it holds */
     struct Chunk { int q, kk, term; };
     std::vector<Chunk> chunks;
@@ -86,6 +89,7 @@ struct TcBatch {
     AtanParams atan;
     long long *dbg = nullptr;
     int dbg_flags = 0;
+    int tune = 0;
 };
 
 cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st);
