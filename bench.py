@@ -47,6 +47,18 @@ def channel_plan(n_gpus):
     return lpf, offs
 
 
+def measured_traffic(engine, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed ncu capture of
+    this very workload (profiles/r01_traffic.json); None when the capture does not match what is being run."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if t.get("engine") == engine and int(t.get("batch_complex_samples", 0)) == n:
+            return float(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -343,7 +355,9 @@ def main():
                     "d2h_bytes_per_step": 2 * C_PER_GPU * k_per_step * world, "pcm_checksum": checksum},
             "roofline": {"bound": "hbm", "kernel": "fir_fm kernel (fused mix+FIR+decimate+derotate+FM)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                         "peak_source": peak_src,
+                         "traffic": measured_traffic({1: "imad", 2: "tc"}.get(bank.engine, "?"), n) if world == 1 else None,
+                         "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms_per_launch": kern_avg_ms, "kernel_share_of_step": kern_ms / ms_total,
                          "int16_mac_per_s": macs / (kern_avg_ms * 1e-3),
                          "note": "path is integer-compute bound at 64 ch x 127 taps (SURVEY.md 8d): HBM fraction is "

@@ -704,10 +704,13 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
         FAIL_TRY(cudaMemcpy(mu.data(), h->d_mu, C * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         FAIL_TRY(cudaMemcpy(lam.data(), h->d_lambda, C * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         h->all_cyclic = true; h->mu_max = 0;
+        unsigned lam_max = 0;
         for (int c = 0; c < C; c++) {
             if (lam[c] == 0) h->all_cyclic = false;
             else if (mu[c] > h->mu_max) h->mu_max = mu[c];
+            if (lam[c] > lam_max) lam_max = lam[c];
         }
+        if (use_tc) tc_plan_reserve_rot(h->tc, h->all_cyclic ? lam_max : 0, h->smem_max);
     }
 #undef FAIL_TRY
     *ph = h;

@@ -49,7 +49,7 @@ constexpr int XF_THREADS = 32 * XF_WARPS;
 /* Warp roles, lowest warp index first: epilogue | transform | MMA issuer. */
 constexpr int EPI_WARP0 = 0;            /* must be a multiple of 4: warp w may only read TMEM lanes 32*(w%4).. */
 constexpr int XF_WARP0 = EPI_WARPS;     /* first transform warp */
-constexpr int MMA_WARPS = 2;            /* MMA issuers: each owns a disjoint set of limb accumulators */
+constexpr int MMA_WARPS = 2;            /* MMA issuers (2 = each owns a disjoint set of limb accumulators) */
 constexpr int MMA_WARP = EPI_WARPS + XF_WARPS;      /* warp index of the first MMA issuer */
 constexpr int TC_THREADS = 32 * (XF_WARPS + MMA_WARPS + EPI_WARPS);
 constexpr int NB_MAX = 4, NT_MAX = 3;
@@ -77,13 +77,15 @@ struct TcKernelParams {
     int total_tiles;
     int C, G, Kp, Q, R;
     int nb_stages, prog_len, prog_split;
+    int rot_lt;             /* ROT_TAB: entries per channel of the shared-memory derotator table */
     float inv_nslab;
     uint32_t a_group_bytes, b_stage_bytes;
     AtanParams atan;
     long long *dbg;         /* optional per-role clock stamps of CTA 0 (bench diagnostics) */
     int dbg_flags;          /* diagnostics only: 1 = skip the epilogue arithmetic, 2 = skip the transform */
     int tune;               /* experiments (GPUCHAN_TC_TUNE): 1 = epilogue polls t_full with nanosleep instead of a suspended
-                               try_wait, 2 = same for the transform's b_empty wait, 4 = generic (select-based) transform loads */
+                               try_wait, 2 = same for the transform's b_empty wait, 4 = generic (select-based) transform loads,
+                               8 = derotator phases from a shared-memory table (ROT_TAB) */
     TcMma prog[TC_PROG_MAX];
 };
 
@@ -120,7 +122,10 @@ __device__ __forceinline__ void split_store(const uint32_t (&w)[8], uint8_t *hi_
 }
 
 
-template <int MODE, bool KEEP_IQ, bool FMA>
+/* ROT_TAB: steady state with short derotator cycles -- every channel's limit cycle (pre-scaled by 4, unrolled
+ * 2 * TC_STEP + 1 entries past its period) sits in shared memory and the epilogue reads the phases instead of
+ * stepping the recurrence. */
+template <int MODE, bool KEEP_IQ, bool FMA, bool ROT_TAB>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_constant__ TcKernelParams p)
 {
     constexpr int ACCS = (MODE == TC_MODE_SUM) ? 2 : 3;
@@ -130,9 +135,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
     __shared__ __align__(8) uint64_t b_full[NB_MAX], b_empty[NB_MAX], t_full[NT_MAX], t_empty[NT_MAX];
     __shared__ uint32_t tmem_base_s;
     __shared__ float2 atan_s[256];
+    __shared__ TcMma prog_s[TC_PROG_MAX];
 
     uint8_t *sA = smem;                                         /* [a_chunks][2 slabs][128][16] */
     uint8_t *sB = smem + p.a_group_bytes;                       /* [NB stages][2 planes][nslab][R][16] */
+    int2 *sR = reinterpret_cast<int2 *>(sB + (size_t)p.nb_stages * p.b_stage_bytes);    /* [TC_CH][rot_lt] 4 * rot (ROT_TAB) */
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);       /* same value, but provably warp-uniform for the compiler */
     const int nslab = p.Kp >> 4;
@@ -150,10 +157,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         uint4 *dst = reinterpret_cast<uint4 *>(sA);
         for (uint32_t i = tid; i < p.a_group_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
         for (int i = tid; i < 256; i += TC_THREADS) atan_s[i] = p.atan_tab[i];
+        for (int i = tid; i < p.prog_len; i += TC_THREADS) prog_s[i] = p.prog[i];
+        if (ROT_TAB) {
+            const int lt = p.rot_lt;                            /* power of two >= longest period + TC_STEP + 1 */
+            for (int i = tid; i < TC_CH * lt; i += TC_THREADS) {
+                const int chn = i / lt, j = i - chn * lt, cc = g * TC_CH + chn;
+                int2 v = make_int2(0, 0);
+                if (cc < p.C) {
+                    const int w = __ldg(p.cyc + (size_t)cc * p.cyc_pitch + (uint32_t)j % __ldg(p.lambda + cc));
+                    v = make_int2(4 * lo16(w), 4 * hi16(w));
+                }
+                sR[chn * (lt + 1) + j] = v;                     /* odd row pitch: the 16 channels of a half-warp hit 16 bank pairs */
+            }
+        }
     }
     if (tid == 0) {
         for (int s = 0; s < NB_MAX; s++) { ptx::mbar_init(&b_full[s], XF_WARPS); ptx::mbar_init(&b_empty[s], MMA_WARPS); }
-        for (int s = 0; s < NT_MAX; s++) { ptx::mbar_init(&t_full[s], MMA_WARPS); ptx::mbar_init(&t_empty[s], EPI_WARPS); }
+        for (int s = 0; s < NT_MAX; s++) { ptx::mbar_init(&t_full[s], MMA_WARPS); ptx::mbar_init(&t_empty[s], EPI_WARPS / 2); }
         ptx::fence_mbar_init();
     }
     if (warp_u == MMA_WARP) ptx::tmem_alloc(&tmem_base_s, 512);
@@ -257,14 +277,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
     } else if (warp_u >= MMA_WARP) {
         /* ================= MMA issuers =================
          * Two warps, each issuing the MMAs of its own accumulators (SUM: the 2^8 / the 2^0 limb; RADIX: limbs
-         * {2^16, 2^0} / {2^8}), so no ordering is needed between them; both commit to the same barriers.  The whole
-         * warp walks the (warp-uniform) loop so that descriptors live in uniform registers; only the tcgen05
-         * instructions themselves are issued by one lane. */
+         * {2^16, 2^0} / {2^8}), so no ordering is needed between them; both commit to the same barriers.
+         * The program is lane resident: lane l of a pass owns one MMA, adds the stage bases to its descriptors with
+         * ordinary vector instructions and issues it itself.  ptxas turns the per-lane tcgen05.mma into a short
+         * ELECT / R2UR.BROADCAST / UTCIMMA loop over the active lanes -- no constant loads and no uniform-datapath
+         * arithmetic per instruction (the previous uniform-register decode took longer than the MMAs themselves).
+         * The first MMA into an accumulator (accumulate = 0) goes out before the others; beyond that the order
+         * of accumulation does not matter. */
         const int mw = warp_u - MMA_WARP;
         const bool leader = lane == 0 && mw == 0;
-        const int i0 = mw == 0 ? 0 : p.prog_split, i1 = mw == 0 ? p.prog_split : p.prog_len;
+        const int i0 = (MMA_WARPS == 1 || mw == 0) ? 0 : p.prog_split, i1 = (MMA_WARPS == 1 || mw != 0) ? p.prog_len : p.prog_split;
         const uint32_t a_base = ptx::smem_u32(sA) >> 4, b_base0 = ptx::smem_u32(sB) >> 4;
         constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);      /* SBO = 128 B, descriptor version 1 (bit 46) */
+        const int passes = (i1 - i0 + 31) >> 5;
+        TcMma m0 = { 0, 0, 0, 0 };
+        const bool have0 = i0 + lane < i1;
+        if (have0) m0 = prog_s[i0 + lane];
         int sb = 0, phb = 0, st = 0, pht = 0;
         for (int it = 0; it < my_tiles; it++) {
             if (leader) DBG(1, it, 0);
@@ -275,13 +303,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             ptx::tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)st * STAGE_COLS;
             const uint32_t b_base = b_base0 + (((uint32_t)sb * p.b_stage_bytes) >> 4);
-#pragma unroll 4
-            for (int i = i0; i < i1; i++) {
-                const TcMma m = p.prog[i];
+            for (int ps = 0; ps < passes; ps++) {
+                TcMma m = m0;
+                bool have = have0;
+                if (ps > 0) {                       /* more than 32 MMAs per warp and tile: fetch the next 32 */
+                    have = i0 + 32 * ps + lane < i1;
+                    if (have) m = prog_s[i0 + 32 * ps + lane];
+                }
                 const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.a_lo + a_base);
                 const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.b_lo + b_base);
                 const uint32_t d = acc + (m.d_acc & 0xffffu);
-                if (ptx::elect_one()) ptx::mma_i8(d, da, db, m.idesc, m.d_acc >> 31);
+                const bool first = (m.d_acc >> 31) == 0;
+                if (have && first) ptx::mma_i8(d, da, db, m.idesc, 0u);
+                __syncwarp();
+                if (have && !first) ptx::mma_i8(d, da, db, m.idesc, 1u);
+                __syncwarp();
             }
             if (ptx::elect_one()) {
                 ptx::mma_commit(&b_empty[sb]);      /* smem stage may be refilled once these MMAs have read it */
@@ -295,18 +331,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
     } else {
         /* ================= epilogue: TMEM -> registers -> derotate -> discriminate -> PCM =================
          * Accumulator row 32*s + i (i < 16) is the real part of channel 16*s + i, row 32*s + 16 + i its imaginary
-         * part.  Warp (s, pair) drains columns TC_LEAD + 16*pair + [-1, 16) with the 16x32bx2 load shape: lanes
-         * 0-15 receive the first 8 columns and lanes 16-31 the last 8 columns of the SAME 16 TMEM lanes, once for the
-         * real rows and once for the imaginary rows, so every thread ends up with both components of its own
-         * channel x 8 outputs -- no shuffles, no selects.
-         * The arithmetic (fm_math.cuh "v2") is arranged for the pipe split of sm_100: ncu showed the previous
+         * part.  The 16 warps form two SETS of 8 that take alternate tiles, so one set's barrier wait and TMEM drain
+         * overlap the other set's arithmetic (with all 16 warps in lock step on one tile the issue ports idled
+         * through every drain).  Inside a set, warp (s, half) turns columns TC_LEAD + 32*half + [0, 32) of its 16
+         * channels into PCM: lanes 0-15 the first 16 columns, lanes 16-31 the last 16, as two consecutive 8-output
+         * blocks.  The 16x32bx2 load shape hands lanes 0-15 and 16-31 different columns of the SAME 16 TMEM lanes,
+         * once for the real rows and once for the imaginary rows, so every thread receives both components of its
+         * own channel x 8 outputs -- no shuffles, no selects.
+         * The arithmetic (fm_math.cuh "v2") is arranged for the pipe split of sm_100: ncu showed the first
          * epilogue bound by the ALU pipe (67 % busy, FMA pipe 24 %), so selects/compares became multiply-adds. */
         const int e = warp - EPI_WARP0;
+        const int set = e >> 3;
         const int slice = warp & 3;
-        const int pair = e >> 2;
+        const int half = (e >> 2) & 1;
         const bool hi = lane >= 16;
         const int ch = 16 * slice + (lane & 15);
-        const int blk = 2 * pair + (hi ? 1 : 0);    /* which 8-output block of the tile this thread turns into PCM */
+        const int blk0 = 4 * half + (hi ? 2 : 0);   /* first of this thread's two 8-output blocks of a tile */
         const uint32_t lane_re = (uint32_t)(32 * slice) << 16, lane_im = (uint32_t)(32 * slice + 16) << 16;
         const int c = g * TC_CH + ch;
         const bool live = c < p.C;
@@ -317,139 +357,178 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         const float z_thr = p.atan.z_small_thr;
         const uint32_t atan_smem = ptx::smem_u32(atan_s);
         /* Steady state (every channel on its limit cycle): the phase of the output before my first one comes from the
-         * channel's cycle table; it advances by TC_OUT outputs per tile. */
+         * channel's cycle table; it advances by 2 * TC_OUT outputs from one of my tiles to the next. */
         const bool table_mode = p.ckpt == nullptr;
         uint32_t lam = 1, tph = 0, tstep = 0;
         const int *tab = nullptr;
         if (table_mode && live) {
             lam = __ldg(p.lambda + c);
-            const unsigned long long g0 = p.k_base + (unsigned long long)TC_OUT * tile0 + 8 * blk - 1 - __ldg(p.mu + c);
+            const unsigned long long g0 = p.k_base + (unsigned long long)TC_OUT * (tile0 + set) + 8 * blk0 - 1 - __ldg(p.mu + c);
             tph = (uint32_t)(g0 % lam);
-            tstep = (uint32_t)TC_OUT % lam;
+            tstep = (uint32_t)(2 * TC_OUT) % lam;
             tab = p.cyc + (size_t)c * p.cyc_pitch;
         }
-        /* derotator phase word of tile `it` of this CTA: the phase of the output before my block (of output 0 itself
-         * for the very first block of the stream segment); fetched one tile ahead so that its latency hides behind
-         * the arithmetic of the current tile */
+        /* derotator phase word of tile `it` of this CTA: the phase of the output before my first block (of output 0
+         * itself for the very first block of the stream segment); fetched one tile ahead so that its latency hides
+         * behind the arithmetic of the current tile */
+        const int2 *const rrow = sR + (size_t)ch * (p.rot_lt + 1);    /* ROT_TAB: this channel's row of the phase table */
         auto phase_word = [&](int it) -> int {
             if (!live) return 0;
             const int tile = tile0 + it;
             if (table_mode) {
                 uint32_t ix = tph;
-                if (tile == 0 && blk == 0) { ix++; if (ix == lam) ix = 0; }
                 tph += tstep;
                 if (tph >= lam) tph -= lam;
+                if (ROT_TAB) return (int)ix;                    /* table index of the phase of output kfirst - 1 */
+                if (tile == 0 && blk0 == 0) { ix++; if (ix == lam) ix = 0; }
                 return __ldg(tab + ix);
             }
-            return __ldg(p.ckpt + ((size_t)tile * TC_SUB + blk) * p.C + c);
+            return __ldg(p.ckpt + ((size_t)tile * TC_SUB + blk0) * p.C + c);
         };
-        int cwk_next = my_tiles > 0 ? phase_word(0) : 0;
+        int cwk_next = set < my_tiles ? phase_word(set) : 0;
+        const bool stamp = tid == 0;
 
-        int st = 0, pht = 0;
-        for (int it = 0; it < my_tiles; it++) {
+        for (int it = set; it < my_tiles; it += 2) {
             const int tile = tile0 + it;
+            const int st = it % NT, pht = (it / NT) & 1;
             const int cwk = cwk_next;
-            if (tid == 0) DBG(2, it, 0);
+            if (stamp) DBG(2, it >> 1, 0);
             if (p.tune & 1) ptx::mbar_wait_backoff(&t_full[st], pht, 32);
             else ptx::mbar_wait_sleep(&t_full[st], pht, 100000);
-            if (tid == 0) DBG(2, it, 1);
+            if (stamp) DBG(2, it >> 1, 1);
             ptx::tc_fence_after();
-            /* ---- drain my 8 columns + the one before them, both components, every limb accumulator ---- */
-            int x_re[8], x_im[8], xl_re, xl_im;     /* 4 * acc + 0x8000 (mod 2^32): top 16 bits = rq14(acc) */
-            {
-                const uint32_t col0 = tmem_base + (uint32_t)st * STAGE_COLS + TC_LEAD + 16 * pair;
-                int a0r[8], a1r[8], a2r[8], a0i[8], a1i[8], a2i[8], l0r, l1r, l2r = 0, l0i, l1i, l2i = 0;
-                ptx::tmem_ld8_split8(col0 + lane_re, a0r);
-                ptx::tmem_ld8_split8(col0 + lane_im, a0i);
-                ptx::tmem_ld8_split8(col0 + lane_re + TC_ACC_STRIDE, a1r);
-                ptx::tmem_ld8_split8(col0 + lane_im + TC_ACC_STRIDE, a1i);
+            const uint32_t col0 = tmem_base + (uint32_t)st * STAGE_COLS + TC_LEAD + 32 * half;
+            /* limb weights: SUM (2^8, 1), RADIX (2^16, 2^8, 1); times 4 and + 0x8000 for the rounding shift */
+            auto comb = [](int a0, int a1, int a2) -> int {
+                if (ACCS == 3) return (int)((unsigned)a2 * 4u + ((unsigned)a1 * 1024u + ((unsigned)a0 * 262144u + 0x8000u)));
+                return (int)((unsigned)a1 * 4u + ((unsigned)a0 * 1024u + 0x8000u));
+            };
+            /* 8 columns starting at `col` (+16 for lanes 16-31), both components, every limb accumulator:
+             * x = 4 * acc + 0x8000 (mod 2^32), top 16 bits = rq14(acc) */
+            auto drain8 = [&](uint32_t col, int (&x_re)[8], int (&x_im)[8]) {
+                int a0r[8], a1r[8], a2r[8], a0i[8], a1i[8], a2i[8];
+                ptx::tmem_ld8_split16(col + lane_re, a0r);
+                ptx::tmem_ld8_split16(col + lane_im, a0i);
+                ptx::tmem_ld8_split16(col + lane_re + TC_ACC_STRIDE, a1r);
+                ptx::tmem_ld8_split16(col + lane_im + TC_ACC_STRIDE, a1i);
                 if (ACCS == 3) {
-                    ptx::tmem_ld8_split8(col0 + lane_re + 2 * TC_ACC_STRIDE, a2r);
-                    ptx::tmem_ld8_split8(col0 + lane_im + 2 * TC_ACC_STRIDE, a2i);
-                }
-                ptx::tmem_ld1_split8(col0 - 1 + lane_re, l0r);
-                ptx::tmem_ld1_split8(col0 - 1 + lane_im, l0i);
-                ptx::tmem_ld1_split8(col0 - 1 + lane_re + TC_ACC_STRIDE, l1r);
-                ptx::tmem_ld1_split8(col0 - 1 + lane_im + TC_ACC_STRIDE, l1i);
-                if (ACCS == 3) {
-                    ptx::tmem_ld1_split8(col0 - 1 + lane_re + 2 * TC_ACC_STRIDE, l2r);
-                    ptx::tmem_ld1_split8(col0 - 1 + lane_im + 2 * TC_ACC_STRIDE, l2i);
+                    ptx::tmem_ld8_split16(col + lane_re + 2 * TC_ACC_STRIDE, a2r);
+                    ptx::tmem_ld8_split16(col + lane_im + 2 * TC_ACC_STRIDE, a2i);
                 }
                 ptx::tmem_ld_wait();
-                /* limb weights: SUM (2^8, 1), RADIX (2^16, 2^8, 1); times 4 and + 0x8000 for the rounding shift */
-                auto comb = [](int a0, int a1, int a2) -> int {
-                    if (ACCS == 3) return (int)((unsigned)a2 * 4u + ((unsigned)a1 * 1024u + ((unsigned)a0 * 262144u + 0x8000u)));
-                    return (int)((unsigned)a1 * 4u + ((unsigned)a0 * 1024u + 0x8000u));
-                };
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     x_re[u] = comb(a0r[u], a1r[u], ACCS == 3 ? a2r[u] : 0);
                     x_im[u] = comb(a0i[u], a1i[u], ACCS == 3 ? a2i[u] : 0);
                 }
-                xl_re = comb(l0r, l1r, l2r);
-                xl_im = comb(l0i, l1i, l2i);
-            }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&t_empty[st]);  /* TMEM stage is free again */
-            if (tid == 0) DBG(2, it, 2);
-            if (++st == NT) { st = 0; pht ^= 1; }
-            if (it + 1 < my_tiles) cwk_next = phase_word(it + 1);
+            };
 
-            /* ---- one channel x 8 consecutive outputs per thread ---- */
-            const long long kfirst = (long long)TC_OUT * tile + 8 * blk;        /* output index of this thread's first column */
-            const int nvalid = (p.K - kfirst > 8) ? 8 : (int)(p.K - kfirst);
-            if (live && nvalid > 0 && !(p.dbg_flags & 1)) {
-                int r_re = lo16(cwk), r_im = hi16(cwk);
-                int p_re, p_im;
-                if (kfirst == 0) {
-                    /* very first output of the submit: y[-1] is carried state; the phase word = phase of output 0 */
-                    const int lw = __ldg(p.last_in + c);
-                    p_re = lo16(lw); p_im = hi16(lw);
-                } else {
-                    /* previous output = the column before my block; the phase word is its phase */
-                    derotate_v2(xl_re >> 16, xl_im >> 16, r_re, r_im, p_re, p_im);
-                    rot_step_v2(r_re, r_im, i4_re, i4_im);
-                }
-                /* EDGE = this block holds the submit's last output (or is cut short by it): also track y[K-1] */
-                auto block8 = [&](auto edge_tag) {
-                    constexpr bool EDGE = decltype(edge_tag)::value;
-                    int pcm[8], l_re = 0, l_im = 0;
-                    float av[8];
-                    float margin = 1.0f;
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        int y_re, y_im;
-                        derotate_v2(x_re[u] >> 16, x_im[u] >> 16, r_re, r_im, y_re, y_im);
-                        rot_step_v2(r_re, r_im, i4_re, i4_im);
-                        const int s_re = (int)((unsigned)y_re * (unsigned)p_re + (unsigned)y_im * (unsigned)p_im);    /* y * conj(prev) */
-                        const int s_im = (int)((unsigned)y_im * (unsigned)p_re - (unsigned)y_re * (unsigned)p_im);
-                        pcm[u] = pcm_from_phi_v2(fast_atan2f_v2<FMA>(s_im, s_re, atan_smem, z_thr), av[u], margin);
-                        if (KEEP_IQ) { if (!EDGE || u < nvalid) iq_c[kfirst + u] = pack16(y_re, y_im); }
-                        p_re = y_re; p_im = y_im;
-                        if (EDGE) { if (u == nvalid - 1) { l_re = y_re; l_im = y_im; } }
+            int r_re = lo16(cwk), r_im = hi16(cwk);
+            const int2 *rp = rrow + (ROT_TAB ? cwk : 0);    /* rp[0] = 4 * phase of output kfirst - 1, rp[1 + u] of output kfirst + u */
+            int p_re = 0, p_im = 0;
+#pragma unroll 1
+            for (int b = 0; b < 2; b++) {
+                int x_re[8], x_im[8];
+                const long long kfirst = (long long)TC_OUT * tile + 8 * (blk0 + b);     /* output index of the block's first column */
+                if (b == 0) {
+                    /* the column before the first block: the discriminator's previous sample */
+                    int l0r, l1r, l2r = 0, l0i, l1i, l2i = 0;
+                    ptx::tmem_ld1_split16(col0 - 1 + lane_re, l0r);
+                    ptx::tmem_ld1_split16(col0 - 1 + lane_im, l0i);
+                    ptx::tmem_ld1_split16(col0 - 1 + lane_re + TC_ACC_STRIDE, l1r);
+                    ptx::tmem_ld1_split16(col0 - 1 + lane_im + TC_ACC_STRIDE, l1i);
+                    if (ACCS == 3) {
+                        ptx::tmem_ld1_split16(col0 - 1 + lane_re + 2 * TC_ACC_STRIDE, l2r);
+                        ptx::tmem_ld1_split16(col0 - 1 + lane_im + 2 * TC_ACC_STRIDE, l2i);
                     }
-                    if (margin < 0.0f) {    /* about 1 block in 4000: some output sits on a float rounding boundary -> FP64 */
-#pragma unroll
-                        for (int u = 0; u < 8; u++) pcm[u] = pcm_from_phi_exact(av[u]);
-                    }
-                    uint32_t out[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) out[u] = ((uint32_t)pcm[2 * u] & 0xffffu) | ((uint32_t)pcm[2 * u + 1] << 16);
-                    if (!EDGE || nvalid == 8) {
-                        *reinterpret_cast<uint4 *>(pcm_c + kfirst) = make_uint4(out[0], out[1], out[2], out[3]);
+                    drain8(col0, x_re, x_im);
+                    if (stamp) DBG(2, it >> 1, 2);
+                    if (it + 2 < my_tiles) cwk_next = phase_word(it + 2);
+                    if (kfirst == 0) {
+                        /* very first output of the submit: y[-1] is carried state; the phase word = phase of output 0 */
+                        const int lw = live ? __ldg(p.last_in + c) : 0;
+                        p_re = lo16(lw); p_im = hi16(lw);
+                    } else if (ROT_TAB) {
+                        const int2 r4 = rp[0];
+                        derotate_r4(comb(l0r, l1r, l2r) >> 16, comb(l0i, l1i, l2i) >> 16, r4.x, r4.y, p_re, p_im);
                     } else {
-#pragma unroll
-                        for (int u = 0; u < 8; u++)
-                            if (u < nvalid) pcm_c[kfirst + u] = (short)(out[u >> 1] >> (16 * (u & 1)));
+                        /* previous output = the column before my block; the phase word is its phase */
+                        derotate_v2(comb(l0r, l1r, l2r) >> 16, comb(l0i, l1i, l2i) >> 16, r_re, r_im, p_re, p_im);
+                        rot_step_v2(r_re, r_im, i4_re, i4_im);
                     }
-                    /* the thread that produced the submit's last output hands y[K-1] to the next submit */
-                    if (EDGE) { if (kfirst + nvalid == p.K) p.last_out[c] = pack16(l_re, l_im); }
-                };
-                if (kfirst + 8 < p.K) block8(std::false_type{});
-                else block8(std::true_type{});
+                } else {
+                    drain8(col0 + 8, x_re, x_im);
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&t_empty[st]);  /* TMEM stage is free again */
+                    rp += 8;
+                }
+
+                /* ---- one channel x 8 consecutive outputs ---- */
+                const int nvalid = (p.K - kfirst > 8) ? 8 : (int)(p.K - kfirst);
+                if (live && nvalid > 0 && !(p.dbg_flags & 1)) {
+                    /* EDGE = this block holds the submit's last output (or is cut short by it): also track y[K-1] */
+                    auto block8 = [&](auto edge_tag) {
+                        constexpr bool EDGE = decltype(edge_tag)::value;
+                        int l_re = 0, l_im = 0;
+                        float phi[8];
+                        /* phase 1: derotate, discriminate -> 8 angles, in two groups of four outputs whose arctangent
+                         * stages run side by side */
+#pragma unroll
+                        for (int g4 = 0; g4 < 2; g4++) {
+                            int sre[4], sim[4];
+                            Atan2Stage as[4];
+                            float ex[4], ey[4];
+#pragma unroll
+                            for (int v = 0; v < 4; v++) {
+                                const int u = 4 * g4 + v;
+                                int y_re, y_im;
+                                if (ROT_TAB) {
+                                    const int2 r4 = rp[1 + u];
+                                    derotate_r4(x_re[u] >> 16, x_im[u] >> 16, r4.x, r4.y, y_re, y_im);
+                                } else {
+                                    derotate_v2(x_re[u] >> 16, x_im[u] >> 16, r_re, r_im, y_re, y_im);
+                                    rot_step_v2(r_re, r_im, i4_re, i4_im);
+                                }
+                                sre[v] = (int)((unsigned)y_re * (unsigned)p_re + (unsigned)y_im * (unsigned)p_im);    /* y * conj(prev) */
+                                sim[v] = (int)((unsigned)y_im * (unsigned)p_re - (unsigned)y_re * (unsigned)p_im);
+                                if (KEEP_IQ) { if (!EDGE || u < nvalid) iq_c[kfirst + u] = pack16(y_re, y_im); }
+                                p_re = y_re; p_im = y_im;
+                                if (EDGE) { if (u == nvalid - 1) { l_re = y_re; l_im = y_im; } }
+                                atan2_stage1(sim[v], sre[v], as[v]);
+                            }
+#pragma unroll
+                            for (int v = 0; v < 4; v++) atan2_stage2(as[v], atan_smem, ex[v], ey[v]);
+#pragma unroll
+                            for (int v = 0; v < 4; v++) phi[4 * g4 + v] = atan2_stage3<FMA>(sim[v], sre[v], as[v], ex[v], ey[v], z_thr);
+                        }
+                        /* phase 2: angles -> PCM */
+                        int pcm[8];
+                        float margin = 1.0f;
+#pragma unroll
+                        for (int u = 0; u < 8; u++) { float a; pcm[u] = pcm_from_phi_v2(phi[u], a, margin); }
+                        if (margin < 0.0f) {    /* about 1 block in 4000: some output sits on a float rounding boundary -> FP64 */
+#pragma unroll
+                            for (int u = 0; u < 8; u++) pcm[u] = pcm_from_phi_exact(__fmul_rn(phi[u], 16384.0f));
+                        }
+                        uint32_t out[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) out[u] = ((uint32_t)pcm[2 * u] & 0xffffu) | ((uint32_t)pcm[2 * u + 1] << 16);
+                        if (!EDGE || nvalid == 8) {
+                            *reinterpret_cast<uint4 *>(pcm_c + kfirst) = make_uint4(out[0], out[1], out[2], out[3]);
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 8; u++)
+                                if (u < nvalid) pcm_c[kfirst + u] = (short)(out[u >> 1] >> (16 * (u & 1)));
+                        }
+                        /* the thread that produced the submit's last output hands y[K-1] to the next submit */
+                        if (EDGE) { if (kfirst + nvalid == p.K) p.last_out[c] = pack16(l_re, l_im); }
+                    };
+                    if (kfirst + 8 < p.K) block8(std::false_type{});
+                    else block8(std::true_type{});
+                }
             }
-            if (tid == 0) DBG(2, it, 4);
+            if (stamp) DBG(2, it >> 1, 4);
         }
     }
 
@@ -567,7 +646,7 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
     if (pl.a_chunks * 256 >= 16384) { pl.why = "tap image too large for the MMA program encoding"; return pl; }
     pl.a_group_bytes = (size_t)pl.a_chunks * 4096;
     pl.b_stage_bytes = (size_t)2 * pl.Kp * pl.R;
-    const size_t static_smem = 2048 + 256 + 256;     /* atan table, barriers, slack */
+    const size_t static_smem = 2048 + 2560 + 512;     /* atan table, MMA program, barriers, slack */
     const long long room = (long long)smem_max - (long long)static_smem - (long long)pl.a_group_bytes - 128;
     long long nb = room / (long long)pl.b_stage_bytes;
     if (nb > NB_MAX) nb = NB_MAX;
@@ -577,6 +656,27 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
     if ((size_t)pl.R * 16 >= (1u << 18)) { pl.why = "tile too tall for the descriptor"; return pl; }
     pl.ok = true;
     return pl;
+}
+
+/* After the derotator cycles are known: keep the longest period's phase table in shared memory if that leaves at
+ * least 3 sample stages (or as many as there were).  lam_max = 0 (some channel has no tabulated cycle) disables it. */
+void tc_plan_reserve_rot(TcPlan &pl, unsigned lam_max, int smem_max)
+{
+    pl.rot_lt = 0;
+    if (!pl.ok || lam_max == 0) return;
+    int lt = 16;
+    while ((unsigned)lt < lam_max + 2 * TC_STEP + 1) lt *= 2;
+    if (lt > 256) return;
+    const size_t tab_bytes = (size_t)TC_CH * (lt + 1) * sizeof(int2);
+    const size_t static_smem = 2048 + 2560 + 512;
+    const long long room = (long long)smem_max - (long long)static_smem - (long long)pl.a_group_bytes - 128 - (long long)tab_bytes;
+    long long nb = room / (long long)pl.b_stage_bytes;
+    if (nb > NB_MAX) nb = NB_MAX;
+    if (nb < 3 && nb < pl.nb_stages) return;
+    if (nb < 2) return;
+    pl.nb_stages = (int)nb;
+    pl.rot_lt = lt;
+    pl.smem_bytes = pl.a_group_bytes + (size_t)pl.nb_stages * pl.b_stage_bytes + tab_bytes + 128;
 }
 
 void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_im, std::vector<uint8_t> &img)
@@ -627,13 +727,20 @@ size_t tc_max_ckpt_tiles(const TcPlan &, long long max_K, int)
     return (size_t)(max_K / TC_OUT + 2);
 }
 
-template <int MODE, bool KEEP_IQ, bool FMA>
+template <int MODE, bool KEEP_IQ, bool FMA, bool ROT_TAB>
 static cudaError_t launch_variant(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(tc_fir_fm_kernel<MODE, KEEP_IQ, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_fir_fm_kernel<MODE, KEEP_IQ, FMA, ROT_TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_fir_fm_kernel<MODE, KEEP_IQ, FMA><<<ctas, TC_THREADS, smem, st>>>(p);
+    tc_fir_fm_kernel<MODE, KEEP_IQ, FMA, ROT_TAB><<<ctas, TC_THREADS, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int MODE, bool KEEP_IQ>
+static cudaError_t launch_variant2(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st, bool fma, bool rot_tab)
+{
+    if (rot_tab) return fma ? launch_variant<MODE, KEEP_IQ, true, true>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, false, true>(p, ctas, smem, st);
+    return fma ? launch_variant<MODE, KEEP_IQ, true, false>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, false, false>(p, ctas, smem, st);
 }
 
 cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st)
@@ -659,13 +766,16 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     /* persistent grid: one CTA per (tile range, channel group), at most one per SM */
     const unsigned ctas = (unsigned)b.geom.chunks * (unsigned)pl.G;
     const bool iq = b.iq_out != nullptr, fma = b.atan.use_fma != 0;
+    /* the phase table needs the steady state (ckpt == nullptr) and room in shared memory (tc_plan_reserve_rot) */
+    /* Measured on B200 (64 ch x 127 taps / D = 100): 0.110 ms with the table, 0.105 ms with the recurrence -- the
+     * 9 LDS.64 per block cost more (LSU queue, shared-memory bandwidth next to the tensor core's operand reads and
+     * the transform's stores) than the 10 integer instructions per output they replace.  Opt-in: GPUCHAN_TC_TUNE |= 8. */
+    const bool rot_tab = b.ckpt == nullptr && pl.rot_lt > 0 && (b.tune & 8);
+    p.rot_lt = rot_tab ? pl.rot_lt : 0;
     const size_t sm = pl.smem_bytes;
-    if (pl.mode == TC_MODE_RADIX) {
-        if (iq) return fma ? launch_variant<TC_MODE_RADIX, true, true>(p, ctas, sm, st) : launch_variant<TC_MODE_RADIX, true, false>(p, ctas, sm, st);
-        return fma ? launch_variant<TC_MODE_RADIX, false, true>(p, ctas, sm, st) : launch_variant<TC_MODE_RADIX, false, false>(p, ctas, sm, st);
-    }
-    if (iq) return fma ? launch_variant<TC_MODE_SUM, true, true>(p, ctas, sm, st) : launch_variant<TC_MODE_SUM, true, false>(p, ctas, sm, st);
-    return fma ? launch_variant<TC_MODE_SUM, false, true>(p, ctas, sm, st) : launch_variant<TC_MODE_SUM, false, false>(p, ctas, sm, st);
+    if (pl.mode == TC_MODE_RADIX)
+        return iq ? launch_variant2<TC_MODE_RADIX, true>(p, ctas, sm, st, fma, rot_tab) : launch_variant2<TC_MODE_RADIX, false>(p, ctas, sm, st, fma, rot_tab);
+    return iq ? launch_variant2<TC_MODE_SUM, true>(p, ctas, sm, st, fma, rot_tab) : launch_variant2<TC_MODE_SUM, false>(p, ctas, sm, st, fma, rot_tab);
 }
 
 } // namespace tslb200

@@ -47,6 +47,7 @@ struct TcPlan {
     size_t a_group_bytes = 0;           /* bytes of one group's tap image */
     size_t b_stage_bytes = 0;           /* bytes of one sample tile (both planes) */
     size_t smem_bytes = 0;
+    int rot_lt = 0;                     /* entries per channel of the in-kernel derotator phase table (0 = none) */
     std::vector<TcMma> prog;            /* the MMAs of one tile: [0, prog_split) issued by MMA warp 0, the rest by warp 1 */
     int prog_split = 0;                 /* the two warps own disjoint accumulators, so their order does not matter */
     /* tap image construction: for image chunk i, which (q, kk) it covers and which limb/term it holds */
@@ -55,6 +56,7 @@ struct TcPlan {
 };
 
 TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_im, int smem_max);
+void tc_plan_reserve_rot(TcPlan &pl, unsigned lam_max, int smem_max);
 /* tap image for all groups: [G][a_chunks][2 slabs][128 rows][16] bytes */
 void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_im, std::vector<uint8_t> &img);
 

@@ -162,6 +162,17 @@ __device__ __forceinline__ void tmem_ld1_split8(uint32_t taddr, int &v)
 {
     asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x1.b32 {%0}, [%1], 8;" : "=r"(v) : "r"(taddr) : "memory");
 }
+/* the same with a half-split offset of 16 columns */
+__device__ __forceinline__ void tmem_ld8_split16(uint32_t taddr, int (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], 16;"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld1_split16(uint32_t taddr, int &v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x1.b32 {%0}, [%1], 16;" : "=r"(v) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 } // namespace ptx
