@@ -472,6 +472,7 @@ struct gpuchan {
     long long *d_dbg = nullptr;             /* role clock stamps (GPUCHAN_DEBUG_STAMPS=1) */
     int nr_sms = 148;
     int tc_tune = 0;                        /* GPUCHAN_TC_TUNE: kernel experiment switches (tc_engine.cu) */
+    uint32_t tc_sleep[3] = { 0, 0, 0 };     /* GPUCHAN_TC_SLEEP="epi,xf,mma" ns: poll intervals (0 = default) */
 };
 
 static void host_atan_table(float2 *out)
@@ -654,6 +655,7 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
             FAIL_TRY(cudaEventCreateWithFlags(&h->ev_main_done[i], cudaEventDisableTiming));
         }
         if (getenv("GPUCHAN_TC_TUNE")) h->tc_tune = atoi(getenv("GPUCHAN_TC_TUNE"));
+        if (getenv("GPUCHAN_TC_SLEEP")) sscanf(getenv("GPUCHAN_TC_SLEEP"), "%u,%u,%u", &h->tc_sleep[0], &h->tc_sleep[1], &h->tc_sleep[2]);
         if (getenv("GPUCHAN_DEBUG_STAMPS")) {
             FAIL_TRY(cudaMalloc(&h->d_dbg, 3 * 32 * 8 * sizeof(long long)));
             FAIL_TRY(cudaMemset(h->d_dbg, 0, 3 * 32 * 8 * sizeof(long long)));
@@ -710,7 +712,7 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
             else if (mu[c] > h->mu_max) h->mu_max = mu[c];
             if (lam[c] > lam_max) lam_max = lam[c];
         }
-        if (use_tc) tc_plan_reserve_rot(h->tc, h->all_cyclic ? lam_max : 0, h->smem_max);
+        if (use_tc && (h->tc_tune & 8)) tc_plan_reserve_rot(h->tc, h->all_cyclic ? lam_max : 0, h->smem_max);
     }
 #undef FAIL_TRY
     *ph = h;
@@ -854,6 +856,7 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
             tb.dbg = h->d_dbg;
             tb.dbg_flags = (h->d_dbg && getenv("GPUCHAN_DEBUG_SKIP")) ? atoi(getenv("GPUCHAN_DEBUG_SKIP")) : 0;
             tb.tune = h->tc_tune;
+            for (int i = 0; i < 3; i++) if (h->tc_sleep[i]) tb.sleep_ns[i] = h->tc_sleep[i];
             CUDA_TRY(tc_launch_fir_fm(h->tc, tb, st));
             h->launches++;
         } else {

@@ -46,6 +46,9 @@ namespace {
 constexpr int EPI_WARPS = 16;
 constexpr int XF_WARPS = 8;             /* transform warps: raw cs16 -> byte planes in smem */
 constexpr int XF_THREADS = 32 * XF_WARPS;
+/* The transform warps form one group per sample stage (warp w -> group w % NB); a group fills its stage on its own,
+ * so NB tiles' loads are in flight at any time.  One group per stage also keeps every barrier wait at most one
+ * phase behind (a parity wait cannot tell phases two apart). */
 /* Warp roles, lowest warp index first: epilogue | transform | MMA issuer. */
 constexpr int EPI_WARP0 = 0;            /* must be a multiple of 4: warp w may only read TMEM lanes 32*(w%4).. */
 constexpr int XF_WARP0 = EPI_WARPS;     /* first transform warp */
@@ -77,14 +80,17 @@ struct TcKernelParams {
     int total_tiles;
     int C, G, Kp, Q, R;
     int nb_stages, prog_len, prog_split;
+    int atan_copies;        /* interleaved copies of the arctangent table in shared memory: 16 or 1 */
     int rot_lt;             /* ROT_TAB: entries per channel of the shared-memory derotator table */
     float inv_nslab;
     uint32_t a_group_bytes, b_stage_bytes;
     AtanParams atan;
     long long *dbg;         /* optional per-role clock stamps of CTA 0 (bench diagnostics) */
     int dbg_flags;          /* diagnostics only: 1 = skip the epilogue arithmetic, 2 = skip the transform */
-    int tune;               /* experiments (GPUCHAN_TC_TUNE): 1 = epilogue polls t_full with nanosleep instead of a suspended
-                               try_wait, 2 = same for the transform's b_empty wait, 4 = generic (select-based) transform loads,
+    uint32_t sleep_epi, sleep_xf, sleep_mma;    /* nanoseconds between polls of a role's barrier wait */
+    int tune;               /* experiments (GPUCHAN_TC_TUNE): 1 = epilogue waits for t_full with a "suspended" try_wait instead of
+                               nanosleep polling (ncu: NANOSLEEP.SYNCS returns at once, the loop spins: 19 % of all issued
+                               instructions), 2 = same for the transform's b_empty wait, 16 = same for the MMA warps, 4 = generic (select-based) transform loads,
                                8 = derotator phases from a shared-memory table (ROT_TAB) */
     TcMma prog[TC_PROG_MAX];
 };
@@ -134,12 +140,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t b_full[NB_MAX], b_empty[NB_MAX], t_full[NT_MAX], t_empty[NT_MAX];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float2 atan_s[256];
     __shared__ TcMma prog_s[TC_PROG_MAX];
 
     uint8_t *sA = smem;                                         /* [a_chunks][2 slabs][128][16] */
     uint8_t *sB = smem + p.a_group_bytes;                       /* [NB stages][2 planes][nslab][R][16] */
-    int2 *sR = reinterpret_cast<int2 *>(sB + (size_t)p.nb_stages * p.b_stage_bytes);    /* [TC_CH][rot_lt] 4 * rot (ROT_TAB) */
+    int2 *sR = reinterpret_cast<int2 *>(sB + (size_t)p.nb_stages * p.b_stage_bytes);    /* [TC_CH][rot_lt + 1] 4 * rot (ROT_TAB) */
+    /* arctangent table, entry-major with atan_copies (16 or 1) interleaved copies: entry i of copy c sits at
+     * (i * copies + c) * 8 bytes, so that with 16 copies lane l (copy l & 15) always reads bank pair l & 15 -- every
+     * table load is two conflict-free wavefronts.  (One shared copy cost 12.8 wavefronts per load on average: the
+     * look-ups alone kept the shared-memory data pipe 30 % busy next to the tensor core's operand reads.) */
+    float2 *sT = reinterpret_cast<float2 *>(reinterpret_cast<uint8_t *>(sR) + (ROT_TAB ? (size_t)TC_CH * (p.rot_lt + 1) * sizeof(int2) : 0));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);       /* same value, but provably warp-uniform for the compiler */
     const int nslab = p.Kp >> 4;
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         const uint4 *src = reinterpret_cast<const uint4 *>(p.tap_img + (size_t)g * p.a_group_bytes);
         uint4 *dst = reinterpret_cast<uint4 *>(sA);
         for (uint32_t i = tid; i < p.a_group_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
-        for (int i = tid; i < 256; i += TC_THREADS) atan_s[i] = p.atan_tab[i];
+        for (int i = tid; i < 256 * p.atan_copies; i += TC_THREADS) sT[i] = p.atan_tab[i / p.atan_copies];
         for (int i = tid; i < p.prog_len; i += TC_THREADS) prog_s[i] = p.prog[i];
         if (ROT_TAB) {
             const int lt = p.rot_lt;                            /* power of two >= longest period + TC_STEP + 1 */
@@ -172,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         }
     }
     if (tid == 0) {
-        for (int s = 0; s < NB_MAX; s++) { ptx::mbar_init(&b_full[s], XF_WARPS); ptx::mbar_init(&b_empty[s], MMA_WARPS); }
+        for (int s = 0; s < NB_MAX; s++) { ptx::mbar_init(&b_full[s], (uint32_t)((XF_WARPS - s + p.nb_stages - 1) / p.nb_stages)); ptx::mbar_init(&b_empty[s], MMA_WARPS); }
         for (int s = 0; s < NT_MAX; s++) { ptx::mbar_init(&t_full[s], MMA_WARPS); ptx::mbar_init(&t_empty[s], EPI_WARPS / 2); }
         ptx::fence_mbar_init();
     }
@@ -185,12 +195,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
 #define DBG(role, it, slot) do { if (p.dbg && blockIdx.x == 0 && (it) < 32) p.dbg[((role) * 32 + (it)) * 8 + (slot)] = clock64(); } while (0)
 
     if (warp_u >= XF_WARP0 && warp_u < XF_WARP0 + XF_WARPS) {
-        const int xt = tid - 32 * XF_WARP0;         /* 0 .. XF_THREADS-1 */
+        const int xall = tid - 32 * XF_WARP0;       /* 0 .. XF_THREADS-1 */
+        const int xw = warp_u - XF_WARP0;
+        const int grp = xw % NB;                    /* this warp's group = the stage it fills: tiles grp, grp + NB, ... of the CTA */
+        const int XG_THREADS = 32 * ((XF_WARPS - grp + NB - 1) / NB);      /* threads in my group */
+        const int xt = 32 * (xw / NB) + lane;       /* 0 .. XG_THREADS-1 inside the group */
         /* ================= transform: raw cs16 samples -> hi/lo byte planes of the smem ring =================
          * Plane row m of tile t = stream samples [(TC_OUT*t - TC_LEAD + m) * D, +D); item (m, j) is one 16-byte slab
          * entry = 8 complex samples = 32 raw bytes.  Consecutive threads take consecutive j: 32-byte pieces of one
          * contiguous run, so the global reads coalesce.  Entries past D in a row multiply zero taps, so the fast path
-         * does not mask them. */
+         * does not mask them.
+         * A tile costs a handful of dependent global-load round trips whatever the number of threads on it (measured:
+         * ~4000 cycles with all 8 warps on one tile, the whole kernel waiting on it), so the 8 warps form one group
+         * per stage that fills it on its own: NB tiles' loads are in flight at any time. */
         const int items = p.R * nslab;
         const uint32_t slab_bytes = (uint32_t)p.R * 16;
         /* L2 prefetch of the TC_OUT new block-rows of a tile (the stream is read from HBM exactly once) */
@@ -205,32 +222,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             const uintptr_t b = reinterpret_cast<uintptr_t>(p.in.fresh + s_b) & ~(uintptr_t)15;
             if (b > a) ptx::prefetch_l2(reinterpret_cast<const void *>(a), (uint32_t)(b - a));
         };
-        if (xt == 0) { prefetch_tile(tile0 + 1); prefetch_tile(tile0 + 2); }
-        int s = 0, ph = 0;
-        for (int it = 0; it < my_tiles; it++) {
-            if (xt == 0) { DBG(0, it, 0); prefetch_tile(tile0 + it + 3); }
-            if (p.tune & 2) ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, 256);
-            else ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1, 100000);
-            if (xt == 0) DBG(0, it, 1);
+        if (xt == 0) prefetch_tile(tile0 + grp + NB);
+        const bool xstamp = xall == 0;
+        for (int it = grp; it < my_tiles; it += NB) {
+            const int s = grp, ph = (it / NB) & 1;
+            if (xstamp) DBG(0, it / NB, 0);
+            if (xt == 0) prefetch_tile(tile0 + it + 2 * NB);
+            if (p.tune & 2) ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1, 100000);
+            else ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, p.sleep_xf);
+            if (xstamp) DBG(0, it / NB, 1);
             uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
             const long long row_base = (long long)TC_OUT * (tile0 + it) - TC_LEAD;
             const long long s_first = row_base * (long long)p.D;
             const long long s_last = s_first + (long long)(p.R - 1) * p.D + 8 * nslab + 12;     /* one past the furthest word read */
             if (p.dbg_flags & 2) {
             } else if (s_first >= p.in.carry_len + 4 && s_last <= p.in.total) {
+                /* a thread keeps one slab column j and walks down the rows: addresses advance by constants, and the
+                 * loads of consecutive rows are independent, so several stay in flight */
                 const int *base = p.in.fresh + (s_first - p.in.carry_len);
                 const uint32_t o_tile = (uint32_t)(reinterpret_cast<uintptr_t>(base) >> 2) & 3u;
-                if ((p.D & 3) == 0 && !(p.tune & 4)) {
+                const int row_lanes = XG_THREADS / nslab;
+                const int j = xt % nslab, rl = xt / nslab;
+                uint8_t *d_hi = dst + (size_t)j * slab_bytes + rl * 16;
+                const size_t lo_off = (size_t)nslab * slab_bytes;
+                if (rl >= row_lanes) {
+                } else if ((p.D & 3) == 0 && !(p.tune & 4)) {
                     /* rows start a multiple of 4 samples apart: every 8-sample item of the tile has the same
                      * misalignment o_tile against 16 bytes, so the word rotation is resolved at compile time */
-                    const uint4 *abase = reinterpret_cast<const uint4 *>(reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)15);
+                    const uint4 *al = reinterpret_cast<const uint4 *>(reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)15) + ((rl * p.D) >> 2) + 2 * j;
+                    const int al_step = (row_lanes * p.D) >> 2;
                     auto run = [&](auto o_tag) {
                         constexpr int O = decltype(o_tag)::value;
 #pragma unroll 4
-                        for (int item = xt; item < items; item += XF_THREADS) {
-                            const int m = __float2int_rz(__fmul_rn((float)item + 0.5f, p.inv_nslab));
-                            const int j = item - m * nslab;
-                            const uint4 *al = abase + ((m * p.D) >> 2) + 2 * j;
+                        for (int m = rl; m < p.R; m += row_lanes) {
                             const uint4 v0 = __ldg(al), v1 = __ldg(al + 1);
                             uint4 v2 = make_uint4(0, 0, 0, 0);
                             if (O) v2 = __ldg(al + 2);
@@ -238,7 +262,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                             uint32_t w[8];
 #pragma unroll
                             for (int u = 0; u < 8; u++) w[u] = c[O + u];
-                            split_store(w, dst + (size_t)j * slab_bytes + m * 16, dst + (size_t)(nslab + j) * slab_bytes + m * 16);
+                            split_store(w, d_hi, d_hi + lo_off);
+                            al += al_step;
+                            d_hi += row_lanes * 16;
                         }
                     };
                     if (o_tile == 0) run(std::integral_constant<int, 0>{});
@@ -246,17 +272,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                     else if (o_tile == 2) run(std::integral_constant<int, 2>{});
                     else run(std::integral_constant<int, 3>{});
                 } else {
+                    const int *src = base + rl * p.D + 8 * j;
 #pragma unroll 4
-                    for (int item = xt; item < items; item += XF_THREADS) {
-                        const int m = __float2int_rz(__fmul_rn((float)item + 0.5f, p.inv_nslab));
-                        const int j = item - m * nslab;
+                    for (int m = rl; m < p.R; m += row_lanes) {
                         uint32_t w[8];
-                        load8_unaligned(base + m * p.D + 8 * j, w);
-                        split_store(w, dst + (size_t)j * slab_bytes + m * 16, dst + (size_t)(nslab + j) * slab_bytes + m * 16);
+                        load8_unaligned(src, w);
+                        split_store(w, d_hi, d_hi + lo_off);
+                        src += row_lanes * p.D;
+                        d_hi += row_lanes * 16;
                     }
                 }
             } else {
-                for (int item = xt; item < items; item += XF_THREADS) {
+                for (int item = xt; item < items; item += XG_THREADS) {
                     const int m = item / nslab, j = item - m * nslab;
                     const long long s0 = (row_base + m) * (long long)p.D + 8 * j;
                     uint32_t w[8];
@@ -268,12 +295,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             ptx::fence_proxy_async();       /* generic-proxy stores -> visible to the tensor core's async proxy */
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&b_full[s]);
-            if (xt == 0) DBG(0, it, 2);
-            if (++s == NB) { s = 0; ph ^= 1; }
+            if (xstamp) DBG(0, it / NB, 2);
         }
         /* keep the tail of the window the next submit still needs (fewer than T samples) */
         if (blockIdx.x == 0 && p.carry_out)
-            for (int i = xt; i < p.carry_keep; i += XF_THREADS) p.carry_out[i] = in_sample(p.in, p.carry_from + i);
+            for (int i = xall; i < p.carry_keep; i += XF_THREADS) p.carry_out[i] = in_sample(p.in, p.carry_from + i);
     } else if (warp_u >= MMA_WARP) {
         /* ================= MMA issuers =================
          * Two warps, each issuing the MMAs of its own accumulators (SUM: the 2^8 / the 2^0 limb; RADIX: limbs
@@ -296,9 +322,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         int sb = 0, phb = 0, st = 0, pht = 0;
         for (int it = 0; it < my_tiles; it++) {
             if (leader) DBG(1, it, 0);
-            ptx::mbar_wait_sleep(&b_full[sb], phb, 200000);
+            if (p.tune & 16) { ptx::mbar_wait_sleep(&b_full[sb], phb, 200000); } else ptx::mbar_wait_backoff(&b_full[sb], phb, p.sleep_mma);
             if (leader) DBG(1, it, 1);
-            ptx::mbar_wait_sleep(&t_empty[st], pht ^ 1, 200000);
+            if (p.tune & 16) { ptx::mbar_wait_sleep(&t_empty[st], pht ^ 1, 200000); } else ptx::mbar_wait_backoff(&t_empty[st], pht ^ 1, p.sleep_mma);
             if (leader) DBG(1, it, 2);
             ptx::tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)st * STAGE_COLS;
@@ -355,7 +381,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         short *const pcm_c = p.pcm + (size_t)c * p.pitch;
         int *const iq_c = KEEP_IQ ? p.iq_out + (size_t)c * p.pitch : nullptr;
         const float z_thr = p.atan.z_small_thr;
-        const uint32_t atan_smem = ptx::smem_u32(atan_s);
+        const uint32_t atan_mul = 8u * (uint32_t)p.atan_copies;
+        const uint32_t atan_smem = ptx::smem_u32(sT) + 8u * ((uint32_t)lane & (uint32_t)(p.atan_copies - 1)) - 0x4B000000u * atan_mul;
         /* Steady state (every channel on its limit cycle): the phase of the output before my first one comes from the
          * channel's cycle table; it advances by 2 * TC_OUT outputs from one of my tiles to the next. */
         const bool table_mode = p.ckpt == nullptr;
@@ -393,8 +420,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             const int st = it % NT, pht = (it / NT) & 1;
             const int cwk = cwk_next;
             if (stamp) DBG(2, it >> 1, 0);
-            if (p.tune & 1) ptx::mbar_wait_backoff(&t_full[st], pht, 32);
-            else ptx::mbar_wait_sleep(&t_full[st], pht, 100000);
+            if (p.tune & 1) ptx::mbar_wait_sleep(&t_full[st], pht, 100000);
+            else ptx::mbar_wait_backoff(&t_full[st], pht, p.sleep_epi);
             if (stamp) DBG(2, it >> 1, 1);
             ptx::tc_fence_after();
             const uint32_t col0 = tmem_base + (uint32_t)st * STAGE_COLS + TC_LEAD + 32 * half;
@@ -498,7 +525,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                                 atan2_stage1(sim[v], sre[v], as[v]);
                             }
 #pragma unroll
-                            for (int v = 0; v < 4; v++) atan2_stage2(as[v], atan_smem, ex[v], ey[v]);
+                            for (int v = 0; v < 4; v++) atan2_stage2(as[v], atan_smem, atan_mul, ex[v], ey[v]);
 #pragma unroll
                             for (int v = 0; v < 4; v++) phi[4 * g4 + v] = atan2_stage3<FMA>(sim[v], sre[v], as[v], ex[v], ey[v], z_thr);
                         }
@@ -646,13 +673,19 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
     if (pl.a_chunks * 256 >= 16384) { pl.why = "tap image too large for the MMA program encoding"; return pl; }
     pl.a_group_bytes = (size_t)pl.a_chunks * 4096;
     pl.b_stage_bytes = (size_t)2 * pl.Kp * pl.R;
-    const size_t static_smem = 2048 + 2560 + 512;     /* atan table, MMA program, barriers, slack */
-    const long long room = (long long)smem_max - (long long)static_smem - (long long)pl.a_group_bytes - 128;
-    long long nb = room / (long long)pl.b_stage_bytes;
-    if (nb > NB_MAX) nb = NB_MAX;
+    const size_t static_smem = 2560 + 512;     /* MMA program, barriers, slack */
+    /* 16 interleaved copies of the arctangent table (32 KB) if at least 3 sample stages still fit, else one (2 KB) */
+    long long nb = 0;
+    for (int copies = 16; copies >= 1; copies /= 16) {
+        const long long room = (long long)smem_max - (long long)static_smem - (long long)pl.a_group_bytes - 128 - 2048LL * copies;
+        nb = room / (long long)pl.b_stage_bytes;
+        if (nb > NB_MAX) nb = NB_MAX;
+        pl.atan_copies = copies;
+        if (nb >= 3) break;
+    }
     if (nb < 2) { pl.why = "tap image + sample ring exceed shared memory"; return pl; }
     pl.nb_stages = (int)nb;
-    pl.smem_bytes = pl.a_group_bytes + (size_t)pl.nb_stages * pl.b_stage_bytes + 128;
+    pl.smem_bytes = pl.a_group_bytes + (size_t)pl.nb_stages * pl.b_stage_bytes + 2048 * (size_t)pl.atan_copies + 128;
     if ((size_t)pl.R * 16 >= (1u << 18)) { pl.why = "tile too tall for the descriptor"; return pl; }
     pl.ok = true;
     return pl;
@@ -668,15 +701,15 @@ void tc_plan_reserve_rot(TcPlan &pl, unsigned lam_max, int smem_max)
     while ((unsigned)lt < lam_max + 2 * TC_STEP + 1) lt *= 2;
     if (lt > 256) return;
     const size_t tab_bytes = (size_t)TC_CH * (lt + 1) * sizeof(int2);
-    const size_t static_smem = 2048 + 2560 + 512;
-    const long long room = (long long)smem_max - (long long)static_smem - (long long)pl.a_group_bytes - 128 - (long long)tab_bytes;
+    const size_t static_smem = 2560 + 512;
+    const long long room = (long long)smem_max - (long long)static_smem - (long long)pl.a_group_bytes - 128 - (long long)tab_bytes - 2048LL * pl.atan_copies;
     long long nb = room / (long long)pl.b_stage_bytes;
     if (nb > NB_MAX) nb = NB_MAX;
     if (nb < 3 && nb < pl.nb_stages) return;
     if (nb < 2) return;
     pl.nb_stages = (int)nb;
     pl.rot_lt = lt;
-    pl.smem_bytes = pl.a_group_bytes + (size_t)pl.nb_stages * pl.b_stage_bytes + tab_bytes + 128;
+    pl.smem_bytes = pl.a_group_bytes + (size_t)pl.nb_stages * pl.b_stage_bytes + tab_bytes + 2048 * (size_t)pl.atan_copies + 128;
 }
 
 void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_im, std::vector<uint8_t> &img)
@@ -762,6 +795,7 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     p.dbg = b.dbg;
     p.dbg_flags = b.dbg_flags;
     p.tune = b.tune;
+    p.sleep_epi = b.sleep_ns[0]; p.sleep_xf = b.sleep_ns[1]; p.sleep_mma = b.sleep_ns[2];
     memcpy(p.prog, pl.prog.data(), pl.prog.size() * sizeof(TcMma));
     /* persistent grid: one CTA per (tile range, channel group), at most one per SM */
     const unsigned ctas = (unsigned)b.geom.chunks * (unsigned)pl.G;
@@ -772,6 +806,7 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
      * the transform's stores) than the 10 integer instructions per output they replace.  Opt-in: GPUCHAN_TC_TUNE |= 8. */
     const bool rot_tab = b.ckpt == nullptr && pl.rot_lt > 0 && (b.tune & 8);
     p.rot_lt = rot_tab ? pl.rot_lt : 0;
+    p.atan_copies = pl.atan_copies;
     const size_t sm = pl.smem_bytes;
     if (pl.mode == TC_MODE_RADIX)
         return iq ? launch_variant2<TC_MODE_RADIX, true>(p, ctas, sm, st, fma, rot_tab) : launch_variant2<TC_MODE_RADIX, false>(p, ctas, sm, st, fma, rot_tab);

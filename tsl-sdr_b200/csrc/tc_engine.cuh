@@ -47,6 +47,7 @@ struct TcPlan {
     size_t a_group_bytes = 0;           /* bytes of one group's tap image */
     size_t b_stage_bytes = 0;           /* bytes of one sample tile (both planes) */
     size_t smem_bytes = 0;
+    int atan_copies = 1;                /* interleaved copies of the arctangent table in shared memory (16 or 1) */
     int rot_lt = 0;                     /* entries per channel of the in-kernel derotator phase table (0 = none) */
     std::vector<TcMma> prog;            /* the MMAs of one tile: [0, prog_split) issued by MMA warp 0, the rest by warp 1 */
     int prog_split = 0;                 /* the two warps own disjoint accumulators, so their order does not matter */
@@ -92,6 +93,7 @@ struct TcBatch {
     long long *dbg = nullptr;
     int dbg_flags = 0;
     int tune = 0;
+    uint32_t sleep_ns[3] = { 200, 1000, 100 };   /* poll intervals: epilogue, transform, MMA issuers */
 };
 
 cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st);
