@@ -161,6 +161,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
     if (my_tiles > p.n_tiles) my_tiles = p.n_tiles;
     if (my_tiles < 0) my_tiles = 0;
 
+    /* L2 prefetch of the TC_OUT new block-rows of a tile (the stream is read from HBM exactly once) */
+    auto prefetch_tile = [&](int t, bool with_lead_in = false) {
+        if (t >= tile0 + my_tiles) return;
+        long long s_a = ((long long)TC_OUT * t + (p.Q - 1)) * (long long)p.D - p.in.carry_len;
+        long long s_b = s_a + (long long)TC_OUT * p.D;
+        const long long n_fresh = p.in.total - p.in.carry_len;
+        if (with_lead_in) { s_a -= (long long)(TC_LEAD + p.Q - 1) * p.D; if (s_a < 0) s_a = 0; }   /* rows the previous tile would have brought in */
+        if (s_a < 0 || s_a >= n_fresh) return;
+        if (s_b > n_fresh) s_b = n_fresh;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p.in.fresh + s_a) & ~(uintptr_t)15;
+        const uintptr_t b = reinterpret_cast<uintptr_t>(p.in.fresh + s_b) & ~(uintptr_t)15;
+        if (b > a) ptx::prefetch_l2(reinterpret_cast<const void *>(a), (uint32_t)(b - a));
+    };
+    /* the first tiles of this CTA are read cold: start their HBM fetches before anything else */
+    if (tid < NB) prefetch_tile(tile0 + tid, tid == 0);
+
     /* ---- one-time setup ---- */
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(p.tap_img + (size_t)g * p.a_group_bytes);
@@ -210,18 +226,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
          * per stage that fills it on its own: NB tiles' loads are in flight at any time. */
         const int items = p.R * nslab;
         const uint32_t slab_bytes = (uint32_t)p.R * 16;
-        /* L2 prefetch of the TC_OUT new block-rows of a tile (the stream is read from HBM exactly once) */
-        auto prefetch_tile = [&](int t) {
-            if (t >= tile0 + my_tiles) return;
-            const long long s_a = ((long long)TC_OUT * t + (p.Q - 1)) * (long long)p.D - p.in.carry_len;
-            long long s_b = s_a + (long long)TC_OUT * p.D;
-            const long long n_fresh = p.in.total - p.in.carry_len;
-            if (s_a < 0 || s_a >= n_fresh) return;
-            if (s_b > n_fresh) s_b = n_fresh;
-            const uintptr_t a = reinterpret_cast<uintptr_t>(p.in.fresh + s_a) & ~(uintptr_t)15;
-            const uintptr_t b = reinterpret_cast<uintptr_t>(p.in.fresh + s_b) & ~(uintptr_t)15;
-            if (b > a) ptx::prefetch_l2(reinterpret_cast<const void *>(a), (uint32_t)(b - a));
-        };
         if (xt == 0) prefetch_tile(tile0 + grp + NB);
         const bool xstamp = xall == 0;
         for (int it = grp; it < my_tiles; it += NB) {
