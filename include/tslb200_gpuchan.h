@@ -47,7 +47,7 @@ extern "C" {
 #define GPUCHAN_F_DEFAULT    GPUCHAN_F_ATAN_FMA
 
 /* kernel selection (engine) */
-#define GPUCHAN_ENGINE_AUTO   0
+#define GPUCHAN_ENGINE_AUTO   0     /* tensor-core engine whenever its plan fits (measured faster even for 1 channel), else IMAD */
 #define GPUCHAN_ENGINE_IMAD   1     /* exact int32 CUDA-core kernel */
 #define GPUCHAN_ENGINE_TC     2     /* exact int8-limb tcgen05 kernel */
 

@@ -193,13 +193,22 @@ def test_tensor_core_engine_shapes(oracle, C, T, D, fs, cut, gain):
         assert np.array_equal(pcm[c], p), f"channel {c} PCM"
 
 
-def test_auto_engine_picks_tensor_cores_for_wide_banks():
+def test_auto_engine_picks_tensor_cores_whenever_the_plan_fits():
+    """AUTO = tensor-core engine for any channel count (measured 5x faster than the IMAD engine even for one channel);
+    the IMAD engine remains for shapes whose tap image and sample ring do not fit shared memory."""
     fs, T, D = 2400000, 127, 100
     lpf = synth.lowpass_taps(T, 9000.0, fs)
     a = GpuChan(lpf, synth.channel_offsets(64, fs), fs, D, 1 << 16)
     b = GpuChan(lpf, synth.channel_offsets(3, fs), fs, D, 1 << 16)
-    assert a.engine == ENGINE_TC and b.engine == ENGINE_IMAD
+    assert a.engine == ENGINE_TC and b.engine == ENGINE_TC
     a.close(); b.close()
+    fs, T, D = 3000000, 2047, 2000          # tap image alone exceeds shared memory -> IMAD fallback, or a clean refusal
+    try:
+        c = GpuChan(synth.lowpass_taps(T, 9000.0, fs), synth.channel_offsets(3, fs), fs, D, 1 << 16)
+        assert c.engine == ENGINE_IMAD
+        c.close()
+    except GpuChanError as exc:
+        assert exc.code == -5
 
 
 @pytest.mark.parametrize("fmt_name", ["cs8", "cu8", "cu8_rtl"])

@@ -615,7 +615,7 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
         free_all(h);
         return set_err(GPUCHAN_E_BADARGS, "unknown engine %u", cfg->engine);
     }
-    if (cfg->engine == GPUCHAN_ENGINE_TC || (cfg->engine == GPUCHAN_ENGINE_AUTO && C >= 32)) {
+    if (cfg->engine == GPUCHAN_ENGINE_TC || (cfg->engine == GPUCHAN_ENGINE_AUTO)) {
         h->tc = tc_make_plan(T, h->D, C, h->h_re.data(), h->h_im.data(), h->smem_max);
         if (h->tc.ok) h->engine = GPUCHAN_ENGINE_TC;
         else if (cfg->engine == GPUCHAN_ENGINE_TC) {
