@@ -250,10 +250,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # one tiny stream per input buffer: it is ordered after the bank's kernels that read that buffer, and the producer
+    # of the buffer's next content (NCCL broadcast / H2D copy on `stream`) waits for it -- so the broadcast of batch
+    # i+1 overlaps the kernel of batch i, but batch i+2 never overwrites what the kernel of batch i still reads
+    readers = [torch.cuda.Stream(device=dev) for _ in range(NB)]
+
     def step_resident(i):
         buf = batches[i % NB]
-        shard.broadcast_iq(dist, buf, src=0)
+        if dist is not None:
+            stream.wait_stream(readers[i % NB])
+            shard.broadcast_iq(dist, buf, src=0)
         bank.submit_device(buf.data_ptr(), n, sptr)
+        if dist is not None:
+            bank.stream_wait(readers[i % NB].cuda_stream)
         k = bank.pending()
         bank.discard()                                  # results stay on the device in this leg
         return k
@@ -304,10 +313,12 @@ def main():
             bank.submit_ptr(pin_in[i % NB].data_ptr(), n)              # pinned H2D inside the C ABI call
         else:
             buf = batches[i % NB]
+            stream.wait_stream(readers[i % NB])
             if rank == 0:
                 buf.copy_(pin_in[i % NB], non_blocking=True)
             shard.broadcast_iq(dist, buf, src=0)
             bank.submit_device(buf.data_ptr(), n, sptr)
+            bank.stream_wait(readers[i % NB].cuda_stream)
 
     def e2e_collect():
         return bank.collect_into(pin_out.data_ptr(), pin_out.shape[1])  # D2H of every channel's PCM, blocking

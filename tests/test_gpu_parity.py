@@ -240,3 +240,31 @@ def test_8bit_formats_widened_on_device(oracle, fmt_name):
         assert pos == n
         got = np.concatenate(got, axis=1)
         assert got.shape == exp_pcm.shape and np.array_equal(got, exp_pcm)
+
+
+@pytest.mark.parametrize("C,T,D,fs,log2n", [(64, 127, 100, 2400000, 25),        # BASELINE configs[1] at bench.py's batch size
+                                            (256, 127, 25, 1200000, 22),         # configs[2] shape
+                                            (1024, 255, 200, 10000000, 23),      # configs[3] shape, all channels on one GPU
+                                            (256, 512, 120, 3000000, 22)])       # configs[4] shape
+def test_full_size_properties(oracle, C, T, D, fs, log2n):
+    """Full-size runs, checked through size-independent properties: (1) the tensor-core engine and the int32 CUDA-core
+    engine -- two independent implementations -- give the same PCM, bit for bit, for every channel; (2) chunk
+    invariance: one submit == three ragged submits; (3) prefix property: the outputs that depend only on the first 2^20
+    input samples equal the CPU oracle's for a handful of channels."""
+    n = 1 << log2n
+    iq = rand_iq(n, seed=log2n * 7 + C)
+    lpf = synth.lowpass_taps(T, min(9000.0, fs / 8), fs)
+    offs = synth.channel_offsets(C, fs)
+    pcm_tc, _, _ = run_bank(lpf, offs, fs, D, iq, flags=F_ATAN_FMA, engine=ENGINE_TC)
+    pcm_im, _, _ = run_bank(lpf, offs, fs, D, iq, flags=F_ATAN_FMA, engine=ENGINE_IMAD)
+    assert pcm_tc.shape == (C, (n - T) // D + 1)
+    assert np.array_equal(pcm_tc, pcm_im), "tensor-core and IMAD engines disagree"
+    cuts = [n // 3 + 17, n // 2 + 4099, n]
+    chunks = [cuts[0], cuts[1] - cuts[0], cuts[2] - cuts[1]]
+    pcm_ck, _, _ = run_bank(lpf, offs, fs, D, iq, chunks=chunks, flags=F_ATAN_FMA, max_batch=max(chunks), engine=ENGINE_TC)
+    assert np.array_equal(pcm_ck, pcm_tc), "chunked stream differs from the one-shot stream"
+    m = 1 << 20
+    k = (m - T) // D + 1
+    for c in sorted({0, C // 3, C - 1}):
+        _, exp = oracle.channel(lpf, offs[c], fs, D, iq[:2 * m])
+        assert np.array_equal(pcm_tc[c, :k], exp[:k]), f"channel {c}: prefix differs from the oracle"

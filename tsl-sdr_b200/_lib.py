@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libtslb200.so")
+LIB_PATH = os.environ.get("TSLB200_LIB") or os.path.join(PKG_DIR, "libtslb200.so")     # TSLB200_LIB: diagnostics builds only
 _lib = None
 
 

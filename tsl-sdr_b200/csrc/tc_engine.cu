@@ -35,6 +35,10 @@
 #include "tc_engine.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef TC_DIAG
+#define TC_DIAG 0       /* diagnostics builds only (tools/gpujob_diag.sh): 1 = no PCM scaling, 2 = no arctangent, 4 = no derotator */
+#endif
+
 #include <cstdio>
 #include <cstring>
 #include <type_traits>
@@ -91,7 +95,7 @@ struct TcKernelParams {
     int tune;               /* experiments (GPUCHAN_TC_TUNE): 1 = epilogue waits for t_full with a "suspended" try_wait instead of
                                nanosleep polling (ncu: NANOSLEEP.SYNCS returns at once, the loop spins: 19 % of all issued
                                instructions), 2 = same for the transform's b_empty wait, 16 = same for the MMA warps, 4 = generic (select-based) transform loads,
-                               8 = derotator phases from a shared-memory table (ROT_TAB) */
+                               8 = derotator phases from a shared-memory table (ROT_TAB), 32 = lane-loop MMA issue only */
     TcMma prog[TC_PROG_MAX];
 };
 
@@ -308,56 +312,89 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         /* ================= MMA issuers =================
          * Two warps, each issuing the MMAs of its own accumulators (SUM: the 2^8 / the 2^0 limb; RADIX: limbs
          * {2^16, 2^0} / {2^8}), so no ordering is needed between them; both commit to the same barriers.
-         * The program is lane resident: lane l of a pass owns one MMA, adds the stage bases to its descriptors with
-         * ordinary vector instructions and issues it itself.  ptxas turns the per-lane tcgen05.mma into a short
-         * ELECT / R2UR.BROADCAST / UTCIMMA loop over the active lanes -- no constant loads and no uniform-datapath
-         * arithmetic per instruction (the previous uniform-register decode took longer than the MMAs themselves).
-         * The first MMA into an accumulator (accumulate = 0) goes out before the others; beyond that the order
-         * of accumulation does not matter. */
+         * Within a warp the first MMA into an accumulator (accumulate = 0) goes out before the others; beyond that
+         * the order of accumulation does not matter. */
         const int mw = warp_u - MMA_WARP;
         const bool leader = lane == 0 && mw == 0;
         const int i0 = (MMA_WARPS == 1 || mw == 0) ? 0 : p.prog_split, i1 = (MMA_WARPS == 1 || mw != 0) ? p.prog_len : p.prog_split;
+        const int n_mine = i1 - i0;
         const uint32_t a_base = ptx::smem_u32(sA) >> 4, b_base0 = ptx::smem_u32(sB) >> 4;
         constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);      /* SBO = 128 B, descriptor version 1 (bit 46) */
-        const int passes = (i1 - i0 + 31) >> 5;
-        TcMma m0 = { 0, 0, 0, 0 };
-        const bool have0 = i0 + lane < i1;
-        if (have0) m0 = prog_s[i0 + lane];
-        int sb = 0, phb = 0, st = 0, pht = 0;
-        for (int it = 0; it < my_tiles; it++) {
-            if (leader) DBG(1, it, 0);
-            if (p.tune & 16) { ptx::mbar_wait_sleep(&b_full[sb], phb, 200000); } else ptx::mbar_wait_backoff(&b_full[sb], phb, p.sleep_mma);
-            if (leader) DBG(1, it, 1);
-            if (p.tune & 16) { ptx::mbar_wait_sleep(&t_empty[st], pht ^ 1, 200000); } else ptx::mbar_wait_backoff(&t_empty[st], pht ^ 1, p.sleep_mma);
-            if (leader) DBG(1, it, 2);
-            ptx::tc_fence_after();
-            const uint32_t acc = tmem_base + (uint32_t)st * STAGE_COLS;
-            const uint32_t b_base = b_base0 + (((uint32_t)sb * p.b_stage_bytes) >> 4);
-            for (int ps = 0; ps < passes; ps++) {
-                TcMma m = m0;
-                bool have = have0;
-                if (ps > 0) {                       /* more than 32 MMAs per warp and tile: fetch the next 32 */
-                    have = i0 + 32 * ps + lane < i1;
-                    if (have) m = prog_s[i0 + 32 * ps + lane];
+        /* NFIX > 0: the warp's whole program (at most NFIX MMAs) stays in registers across the tile loop -- read once
+         * from the parameter block with warp-uniform indices, so ptxas keeps it on the uniform datapath and an MMA
+         * costs two uniform adds and the UTCIMMA itself.  With everything else compiled out the tile pipeline ran
+         * at 3000 cycles per tile on the lane loop (183 cycles per MMA, mostly R2UR latency) against 55 cycles of
+         * tensor-pipe time per MMA.  NFIX = 0: longer programs keep the lane loop. */
+        auto mma_role = [&](auto nfix_tag) {
+            constexpr int NFIX = decltype(nfix_tag)::value;
+            constexpr int NARR = NFIX > 0 ? NFIX : 1;
+            uint32_t fa[NARR], fb[NARR], fd[NARR], fi[NARR];
+            if (NFIX > 0) {
+#pragma unroll
+                for (int i = 0; i < NARR; i++) {
+                    const TcMma m = p.prog[i < n_mine ? i0 + i : i0];
+                    fa[i] = m.a_lo + a_base; fb[i] = m.b_lo; fd[i] = m.d_acc; fi[i] = m.idesc;
                 }
-                const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.a_lo + a_base);
-                const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.b_lo + b_base);
-                const uint32_t d = acc + (m.d_acc & 0xffffu);
-                const bool first = (m.d_acc >> 31) == 0;
-                if (have && first) ptx::mma_i8(d, da, db, m.idesc, 0u);
-                __syncwarp();
-                if (have && !first) ptx::mma_i8(d, da, db, m.idesc, 1u);
-                __syncwarp();
             }
-            if (ptx::elect_one()) {
-                ptx::mma_commit(&b_empty[sb]);      /* smem stage may be refilled once these MMAs have read it */
-                ptx::mma_commit(&t_full[st]);       /* accumulators complete */
+            const int passes = (n_mine + 31) >> 5;
+            TcMma m0 = { 0, 0, 0, 0 };
+            const bool have0 = i0 + lane < i1;
+            if (NFIX == 0 && have0) m0 = prog_s[i0 + lane];
+            int sb = 0, phb = 0, st = 0, pht = 0;
+            for (int it = 0; it < my_tiles; it++) {
+                if (leader) DBG(1, it, 0);
+                if (p.tune & 16) { ptx::mbar_wait_sleep(&b_full[sb], phb, 200000); } else ptx::mbar_wait_backoff(&b_full[sb], phb, p.sleep_mma);
+                if (leader) DBG(1, it, 1);
+                if (p.tune & 16) { ptx::mbar_wait_sleep(&t_empty[st], pht ^ 1, 200000); } else ptx::mbar_wait_backoff(&t_empty[st], pht ^ 1, p.sleep_mma);
+                if (leader) DBG(1, it, 2);
+                ptx::tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)st * STAGE_COLS;
+                const uint32_t b_base = b_base0 + (((uint32_t)sb * p.b_stage_bytes) >> 4);
+                if (NFIX > 0) {
+                    if (ptx::elect_one()) {
+#pragma unroll
+                        for (int i = 0; i < NARR; i++) {
+                            if (i < n_mine)
+                                ptx::mma_i8(acc + (fd[i] & 0xffffu), ((uint64_t)DESC_HI << 32) | (uint64_t)fa[i],
+                                            ((uint64_t)DESC_HI << 32) | (uint64_t)(fb[i] + b_base), fi[i], fd[i] >> 31);
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    /* lane-resident program: lane l of a pass owns one MMA and issues it itself (ptxas emits an
+                     * ELECT / R2UR.BROADCAST / UTCIMMA loop over the active lanes).  The first MMA into an
+                     * accumulator (accumulate = 0) goes out before the others. */
+                    for (int ps = 0; ps < passes; ps++) {
+                        TcMma m = m0;
+                        bool have = have0;
+                        if (ps > 0) {                       /* more than 32 MMAs per warp and tile: fetch the next 32 */
+                            have = i0 + 32 * ps + lane < i1;
+                            if (have) m = prog_s[i0 + 32 * ps + lane];
+                        }
+                        const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.a_lo + a_base);
+                        const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.b_lo + b_base);
+                        const uint32_t d = acc + (m.d_acc & 0xffffu);
+                        const bool first = (m.d_acc >> 31) == 0;
+                        if (have && first) ptx::mma_i8(d, da, db, m.idesc, 0u);
+                        __syncwarp();
+                        if (have && !first) ptx::mma_i8(d, da, db, m.idesc, 1u);
+                        __syncwarp();
+                    }
+                }
+                if (ptx::elect_one()) {
+                    ptx::mma_commit(&b_empty[sb]);      /* smem stage may be refilled once these MMAs have read it */
+                    ptx::mma_commit(&t_full[st]);       /* accumulators complete */
+                }
+                if (leader) DBG(1, it, 4);
+                __syncwarp();
+                if (++sb == NB) { sb = 0; phb ^= 1; }
+                if (++st == NT) { st = 0; pht ^= 1; }
             }
-            if (leader) DBG(1, it, 4);
-            __syncwarp();
-            if (++sb == NB) { sb = 0; phb ^= 1; }
-            if (++st == NT) { st = 0; pht ^= 1; }
-        }
+        };
+        if (p.tune & 32) mma_role(std::integral_constant<int, 0>{});
+        else if (n_mine <= 12) mma_role(std::integral_constant<int, 12>{});
+        else if (n_mine <= 24) mma_role(std::integral_constant<int, 24>{});
+        else mma_role(std::integral_constant<int, 0>{});
     } else {
         /* ================= epilogue: TMEM -> registers -> derotate -> discriminate -> PCM =================
          * Accumulator row 32*s + i (i < 16) is the real part of channel 16*s + i, row 32*s + 16 + i its imaginary
@@ -514,6 +551,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                             for (int v = 0; v < 4; v++) {
                                 const int u = 4 * g4 + v;
                                 int y_re, y_im;
+#if TC_DIAG & 4     /* diagnostics build: no derotator */
+                                y_re = x_re[u] >> 16; y_im = x_im[u] >> 16;
+#else
                                 if (ROT_TAB) {
                                     const int2 r4 = rp[1 + u];
                                     derotate_r4(x_re[u] >> 16, x_im[u] >> 16, r4.x, r4.y, y_re, y_im);
@@ -521,23 +561,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                                     derotate_v2(x_re[u] >> 16, x_im[u] >> 16, r_re, r_im, y_re, y_im);
                                     rot_step_v2(r_re, r_im, i4_re, i4_im);
                                 }
+#endif
                                 sre[v] = (int)((unsigned)y_re * (unsigned)p_re + (unsigned)y_im * (unsigned)p_im);    /* y * conj(prev) */
                                 sim[v] = (int)((unsigned)y_im * (unsigned)p_re - (unsigned)y_re * (unsigned)p_im);
                                 if (KEEP_IQ) { if (!EDGE || u < nvalid) iq_c[kfirst + u] = pack16(y_re, y_im); }
                                 p_re = y_re; p_im = y_im;
                                 if (EDGE) { if (u == nvalid - 1) { l_re = y_re; l_im = y_im; } }
+#if !(TC_DIAG & 2)
                                 atan2_stage1(sim[v], sre[v], as[v]);
+#endif
                             }
 #pragma unroll
+#if TC_DIAG & 2     /* diagnostics build: no arctangent */
+                            for (int v = 0; v < 4; v++) phi[4 * g4 + v] = (float)(sim[v] ^ sre[v]) * 1e-9f;
+#else
                             for (int v = 0; v < 4; v++) atan2_stage2(as[v], atan_smem, atan_mul, ex[v], ey[v]);
 #pragma unroll
                             for (int v = 0; v < 4; v++) phi[4 * g4 + v] = atan2_stage3<FMA>(sim[v], sre[v], as[v], ex[v], ey[v], z_thr);
+#endif
                         }
                         /* phase 2: angles -> PCM */
                         int pcm[8];
                         float margin = 1.0f;
 #pragma unroll
+#if TC_DIAG & 1     /* diagnostics build: no exact PCM scaling */
+                        for (int u = 0; u < 8; u++) pcm[u] = __float2int_rz(phi[u] * 5215.0f);
+#else
                         for (int u = 0; u < 8; u++) { float a; pcm[u] = pcm_from_phi_v2(phi[u], a, margin); }
+#endif
                         if (margin < 0.0f) {    /* about 1 block in 4000: some output sits on a float rounding boundary -> FP64 */
 #pragma unroll
                             for (int u = 0; u < 8; u++) pcm[u] = pcm_from_phi_exact(__fmul_rn(phi[u], 16384.0f));
