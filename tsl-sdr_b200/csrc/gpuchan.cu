@@ -183,9 +183,13 @@ __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict
     int r_re = lo16(rot_state[c]), r_im = hi16(rot_state[c]);
     unsigned long long cur = k0;                 /* (r_re, r_im) == rot at output index cur */
 
+    bool have_ph = false;                        /* on the cycle: phase index of output `cur`, advanced incrementally */
+    uint32_t ph = 0;
     auto seek = [&](unsigned long long g) {
         if (lam != 0 && g >= (unsigned long long)m) {
-            const int w = tab[(g - m) % lam];
+            if (!have_ph) { ph = (uint32_t)((g - m) % lam); have_ph = true; }       /* one 64-bit division per channel */
+            else { const unsigned long long d = g - cur; ph = (uint32_t)((ph + (d < lam ? d : d % lam)) % lam); }
+            const int w = tab[ph];
             r_re = lo16(w); r_im = hi16(w);
         } else {
             while (cur < g) { rot_step(r_re, r_im, i_re, i_im); cur++; }
