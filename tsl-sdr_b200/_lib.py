@@ -80,6 +80,7 @@ def _declare(L: C.CDLL) -> None:
     L.gpuchan_host_free.argtypes = [vp]
     L.gpuchan_debug_stamps.argtypes = [vp, vp]
     L.gpuchan_tc_selftest.argtypes = [vp, vp, vp, vp] + [C.c_int] * 9 + [vp]
+    L.gpuchan_tc_plan_query.argtypes = [C.POINTER(GpuChanCfg), C.c_uint32, vp, vp, sz, vp, sz]
     L.gpuchan_math_selftest.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, vp]
     L.gpuchan_discard.argtypes = [vp]
     L.gpuchan_timing_enable.argtypes = [vp, C.c_int]
@@ -112,7 +113,7 @@ ON_MSG = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint32, C.
 EXPORTS = ["gpuchan_prepare_taps", "gpuchan_derot_increment", "gpuchan_db_to_gain", "gpuchan_create",
            "gpuchan_destroy", "gpuchan_submit", "gpuchan_submit_device", "gpuchan_submit_bytes", "gpuchan_sync", "gpuchan_pending",
            "gpuchan_collect", "gpuchan_collect_iq", "gpuchan_device_pcm", "gpuchan_get_taps",
-           "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error", "gpuchan_timing_enable", "gpuchan_in_flight", "gpuchan_discard", "gpuchan_host_alloc", "gpuchan_host_free", "gpuchan_tc_selftest", "gpuchan_math_selftest", "gpuchan_debug_stamps", "gpuchan_stream_wait",
+           "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error", "gpuchan_timing_enable", "gpuchan_in_flight", "gpuchan_discard", "gpuchan_host_alloc", "gpuchan_host_free", "gpuchan_tc_selftest", "gpuchan_math_selftest", "gpuchan_tc_plan_query", "gpuchan_debug_stamps", "gpuchan_stream_wait",
            "gpuchan_timing_read",
            "gpupager_quantize_taps", "gpupager_create", "gpupager_destroy", "gpupager_feed_device", "gpupager_feed",
            "gpupager_dispatch", "gpupager_dispatch_flex", "gpupager_poll", "gpupager_collect_pcm", "gpupager_kernel_launches",

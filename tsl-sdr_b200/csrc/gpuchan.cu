@@ -519,6 +519,41 @@ extern "C" int gpuchan_math_selftest(uint32_t what, uint64_t seed_or_first, uint
     return GPUCHAN_OK;
 }
 
+/* Host-only view of the tensor-core plan (no device needed): lets the CPU test-suite check the int8 limb
+ * decomposition, the tap image and the per-tile MMA program by emulating them against the direct integer FIR. */
+extern "C" int gpuchan_tc_plan_query(const gpuchan_cfg *cfg, uint32_t smem_max_bytes, uint32_t info[16],
+                                     uint8_t *tap_image, size_t tap_image_cap, uint32_t *program, size_t program_cap_entries)
+{
+    if (!cfg || !info || cfg->struct_size != sizeof(gpuchan_cfg) || !cfg->lpf_taps || !cfg->offset_hz || !cfg->nr_channels ||
+        cfg->nr_taps < 2 || !cfg->decimation || !cfg->sample_rate_hz)
+        return set_err(GPUCHAN_E_BADARGS, "incomplete configuration");
+    const int T = (int)cfg->nr_taps, C = (int)cfg->nr_channels;
+    std::vector<int16_t> re((size_t)C * T), im((size_t)C * T);
+    for (int c = 0; c < C; c++)
+        gpuchan_prepare_taps(cfg->lpf_taps, T, cfg->offset_hz[c], cfg->sample_rate_hz, cfg->gain ? cfg->gain[c] : 1.0,
+                             &re[(size_t)c * T], &im[(size_t)c * T]);
+    const TcPlan pl = tc_make_plan(T, (int)cfg->decimation, C, re.data(), im.data(), smem_max_bytes ? (int)smem_max_bytes : 232448);
+    memset(info, 0, 16 * sizeof(uint32_t));
+    info[0] = pl.ok ? 1u : 0u;
+    if (!pl.ok) return set_err(GPUCHAN_E_INVAL, "tensor-core engine unavailable: %s", pl.why);
+    info[1] = (uint32_t)pl.mode; info[2] = (uint32_t)pl.accs; info[3] = (uint32_t)pl.nb_stages; info[4] = (uint32_t)pl.nt_stages;
+    info[5] = (uint32_t)pl.a_chunks; info[6] = (uint32_t)pl.a_group_bytes; info[7] = (uint32_t)pl.b_stage_bytes;
+    info[8] = (uint32_t)pl.smem_bytes; info[9] = (uint32_t)pl.atan_copies; info[10] = (uint32_t)pl.prog.size();
+    info[11] = (uint32_t)pl.prog_split; info[12] = (uint32_t)pl.Kp; info[13] = (uint32_t)pl.Q; info[14] = (uint32_t)pl.R;
+    info[15] = (uint32_t)pl.G;
+    if (tap_image) {
+        std::vector<uint8_t> img;
+        tc_build_tap_image(pl, re.data(), im.data(), img);
+        if (img.size() > tap_image_cap) return set_err(GPUCHAN_E_BADARGS, "tap image needs %zu bytes", img.size());
+        memcpy(tap_image, img.data(), img.size());
+    }
+    if (program) {
+        if (pl.prog.size() > program_cap_entries) return set_err(GPUCHAN_E_BADARGS, "program has %zu entries", pl.prog.size());
+        memcpy(program, pl.prog.data(), pl.prog.size() * sizeof(TcMma));
+    }
+    return GPUCHAN_OK;
+}
+
 static int free_all(gpuchan *h)
 {
     if (!h) return 0;
