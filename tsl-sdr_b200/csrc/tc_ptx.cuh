@@ -1,6 +1,6 @@
 /*
  * tc_ptx.cuh -- thin inline-PTX wrappers for the sm_100a features the tensor-core engine uses:
- * mbarrier, 1-D bulk async copy (cp.async.bulk -> SASS UBLKCP), TMEM allocation, tcgen05.mma kind::i8
+ * mbarrier, L2 bulk prefetch (cp.async.bulk.prefetch.L2 -> SASS UBLKPF), TMEM allocation, tcgen05.mma kind::i8
  * (SASS UTCIMMA), tcgen05.commit, tcgen05.ld (SASS LDTM).
  */
 #pragma once
@@ -41,11 +41,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
-                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
@@ -71,13 +66,6 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, 
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns)
 {
     while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
-}
-
-/* ---- 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier ---- */
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 /* ask L2 to fetch [p, p + bytes) (16-byte aligned, multiple of 16) ahead of the loads that will want it */
@@ -143,26 +131,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16])
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_ld1(uint32_t taddr, int &v)
-{
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
-}
-/* TMEM -> registers, shape 16x32bx2 with a half-split offset of 8 columns: threads 0-15 of the warp receive
- * columns [c, c + 8) of TMEM lanes L .. L + 15, threads 16-31 columns [c + 8, c + 16) of the SAME 16 lanes
+/* TMEM -> registers, shape 16x32bx2 with a half-split offset of 16 columns: threads 0-15 of the warp receive
+ * columns [c, c + 8) of TMEM lanes L .. L + 15, threads 16-31 columns [c + 16, c + 24) of the SAME 16 lanes
  * (L = lane field of taddr: the warp's 32-lane slice, optionally + 16).  Measured with tools/tmem_probe.cu.
- * This hands every thread the 8 columns it owns without any shuffle or select. */
-__device__ __forceinline__ void tmem_ld8_split8(uint32_t taddr, int (&v)[8])
-{
-    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], 8;"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr) : "memory");
-}
-/* one column per thread: column c for threads 0-15, column c + 8 for threads 16-31 */
-__device__ __forceinline__ void tmem_ld1_split8(uint32_t taddr, int &v)
-{
-    asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x1.b32 {%0}, [%1], 8;" : "=r"(v) : "r"(taddr) : "memory");
-}
-/* the same with a half-split offset of 16 columns */
+ * This hands every thread the columns it owns, for the real and for the imaginary rows, without any shuffle or
+ * select. */
 __device__ __forceinline__ void tmem_ld8_split16(uint32_t taddr, int (&v)[8])
 {
     asm volatile("tcgen05.ld.sync.aligned.16x32bx2.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], 16;"
