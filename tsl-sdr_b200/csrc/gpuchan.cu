@@ -173,7 +173,7 @@ __device__ __forceinline__ long long ckpt_local(const CkptGeom &gm, int t, int r
 __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict__ rot_state, int nr_channels,
                                    const uint32_t *__restrict__ mu, const uint32_t *__restrict__ lambda,
                                    const int *__restrict__ cyc, unsigned long long k0, unsigned long long K,
-                                   CkptGeom gm, int nr_tiles, int *__restrict__ ckpt)
+                                   CkptGeom gm, int nr_tiles, int *__restrict__ ckpt, int transient_only)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nr_channels) return;
@@ -185,10 +185,15 @@ __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict
 
     bool have_ph = false;                        /* on the cycle: phase index of output `cur`, advanced incrementally */
     uint32_t ph = 0;
+    const uint32_t step8 = lam ? (uint32_t)TC_STEP % lam : 0;       /* the usual distance between two checkpoints */
     auto seek = [&](unsigned long long g) {
         if (lam != 0 && g >= (unsigned long long)m) {
             if (!have_ph) { ph = (uint32_t)((g - m) % lam); have_ph = true; }       /* one 64-bit division per channel */
-            else { const unsigned long long d = g - cur; ph = (uint32_t)((ph + (d < lam ? d : d % lam)) % lam); }
+            else {
+                const unsigned long long d = g - cur;
+                ph += (d == (unsigned long long)TC_STEP) ? step8 : (uint32_t)(d % lam);
+                if (ph >= lam) ph -= lam;
+            }
             const int w = tab[ph];
             r_re = lo16(w); r_im = hi16(w);
         } else {
@@ -197,11 +202,15 @@ __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict
         cur = g;
     };
 
-    for (int t = 0; t < nr_tiles; t++)
+    /* checkpoints at or past the start of a tabulated cycle are independent look-ups: rot_prepass_table_kernel fills
+     * them in parallel (transient_only), this thread only walks the transient */
+    bool on_cycle = false;
+    for (int t = 0; t < nr_tiles && !on_cycle; t++)
         for (int r = 0; r < gm.sub; r++) {
             const long long loc = ckpt_local(gm, t, r);
             if (loc < 0 || (unsigned long long)loc > K) continue;   /* unused, or past the last output of this submit: never
                                                    read, and the sequential walk must not overshoot the state we hand on */
+            if (transient_only && lam != 0 && k0 + (unsigned long long)loc >= (unsigned long long)m) { on_cycle = true; break; }
             seek(k0 + (unsigned long long)loc);
             ckpt[((size_t)t * gm.sub + r) * nr_channels + c] = pack16(r_re, r_im);
         }
@@ -214,11 +223,14 @@ __global__ void rot_prepass_kernel(const int *__restrict__ incr, int *__restrict
 __global__ void rot_prepass_table_kernel(int *__restrict__ rot_state, int nr_channels, const uint32_t *__restrict__ mu,
                                          const uint32_t *__restrict__ lambda, const int *__restrict__ cyc,
                                          unsigned long long k0, unsigned long long K, CkptGeom gm,
-                                         int nr_tiles, int *__restrict__ ckpt)
+                                         int nr_tiles, int *__restrict__ ckpt, int cycle_part_only)
 {
+    /* cycle_part_only: some channels are still in their transient (or have no tabulated cycle); fill only the
+     * checkpoints at or past the start of a channel's cycle and leave rot_state to rot_prepass_kernel */
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nr_channels) return;
     const uint32_t m = mu[c], lam = lambda[c];
+    if (lam == 0) return;
     const int *tab = cyc + (size_t)c * ROT_LMAX;
     const int t_begin = blockIdx.y * 16;
     const int t_end = min(nr_tiles, t_begin + 16);
@@ -231,12 +243,13 @@ __global__ void rot_prepass_table_kernel(int *__restrict__ rot_state, int nr_cha
             const long long loc = ckpt_local(gm, t, r);
             if (loc < 0) continue;
             const unsigned long long g = k0 + (unsigned long long)loc;
+            if (g < (unsigned long long)m) continue;
             if (!have) { ph = (uint32_t)((g - m) % lam); have = true; }       /* one 64-bit division per thread */
             else ph = (ph + (uint32_t)(g - prev)) % lam;
             prev = g;
             ckpt[((size_t)t * gm.sub + r) * nr_channels + c] = tab[ph];
         }
-    if (blockIdx.y == 0) rot_state[c] = tab[(k0 + K - m) % lam];
+    if (blockIdx.y == 0 && !cycle_part_only) rot_state[c] = tab[(k0 + K - m) % lam];
 }
 
 /* rot_state[c] = phase at output index k, for banks whose checkpoints come straight from the table */
@@ -843,12 +856,17 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
         } else if (steady) {
             dim3 g((h->C + 63) / 64, (nr_tiles + 15) / 16);
             rot_prepass_table_kernel<<<g, 64, 0, pre>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, cg,
-                                                        nr_tiles, ckpt);
+                                                        nr_tiles, ckpt, 0);
             h->launches++;
         } else {
+            /* some channel is still in its transient: walk that part sequentially (one thread per channel), fill
+             * everything on a tabulated cycle in parallel */
+            dim3 g((h->C + 63) / 64, (nr_tiles + 15) / 16);
+            rot_prepass_table_kernel<<<g, 64, 0, pre>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, cg,
+                                                        nr_tiles, ckpt, 1);
             rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, pre>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
-                                                                 h->k_total, K, cg, nr_tiles, ckpt);
-            h->launches++;
+                                                                 h->k_total, K, cg, nr_tiles, ckpt, 1);
+            h->launches += 2;
         }
         CUDA_TRY(cudaGetLastError());
     }
