@@ -83,7 +83,7 @@ struct TcKernelParams {
     int n_tiles;            /* tiles per CTA */
     int total_tiles;
     int C, G, Kp, Q, R;
-    int nb_stages, prog_len, prog_split;
+    int nb_stages, prog_len, prog_split, prog_regular;
     int atan_copies;        /* interleaved copies of the arctangent table in shared memory: 16 or 1 */
     int rot_lt;             /* ROT_TAB: entries per channel of the shared-memory derotator table */
     float inv_nslab;
@@ -328,14 +328,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         auto mma_role = [&](auto nfix_tag) {
             constexpr int NFIX = decltype(nfix_tag)::value;
             constexpr int NARR = NFIX > 0 ? NFIX : 1;
-            uint32_t fa[NARR], fb[NARR], fd[NARR], fi[NARR];
+            /* per MMA only the two operand offsets differ; accumulator and instruction descriptor alternate between
+             * the values of entry 0 (even entries) and entry 1 (odd entries) -- checked by tc_make_plan */
+            uint32_t fa[NARR], fb[NARR];
+            uint32_t d_even = 0, d_odd = 0, i_even = 0, i_odd = 0;
             if (NFIX > 0) {
 #pragma unroll
                 for (int i = 0; i < NARR; i++) {
                     const TcMma m = p.prog[i < n_mine ? i0 + i : i0];
-                    fa[i] = m.a_lo + a_base; fb[i] = m.b_lo; fd[i] = m.d_acc; fi[i] = m.idesc;
+                    fa[i] = m.a_lo + a_base; fb[i] = m.b_lo;
                 }
+                const TcMma m0 = p.prog[i0], m1 = p.prog[n_mine > 1 ? i0 + 1 : i0];
+                d_even = m0.d_acc & 0xffffu; i_even = m0.idesc; d_odd = m1.d_acc & 0xffffu; i_odd = m1.idesc;
             }
+            const bool odd_is_new_acc = d_odd != d_even;
             const int passes = (n_mine + 31) >> 5;
             TcMma m0 = { 0, 0, 0, 0 };
             const bool have0 = i0 + lane < i1;
@@ -355,8 +361,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
 #pragma unroll
                         for (int i = 0; i < NARR; i++) {
                             if (i < n_mine)
-                                ptx::mma_i8(acc + (fd[i] & 0xffffu), ((uint64_t)DESC_HI << 32) | (uint64_t)fa[i],
-                                            ((uint64_t)DESC_HI << 32) | (uint64_t)(fb[i] + b_base), fi[i], fd[i] >> 31);
+                                ptx::mma_i8(acc + ((i & 1) ? d_odd : d_even), ((uint64_t)DESC_HI << 32) | (uint64_t)fa[i],
+                                            ((uint64_t)DESC_HI << 32) | (uint64_t)(fb[i] + b_base), (i & 1) ? i_odd : i_even,
+                                            (i == 0 || (i == 1 && odd_is_new_acc)) ? 0u : 1u);
                         }
                     }
                     __syncwarp();
@@ -391,7 +398,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                 if (++st == NT) { st = 0; pht ^= 1; }
             }
         };
-        if (p.tune & 32) mma_role(std::integral_constant<int, 0>{});
+        if ((p.tune & 32) || !p.prog_regular) mma_role(std::integral_constant<int, 0>{});
         else if (n_mine <= 12) mma_role(std::integral_constant<int, 12>{});
         else if (n_mine <= 24) mma_role(std::integral_constant<int, 24>{});
         else mma_role(std::integral_constant<int, 0>{});
@@ -721,6 +728,17 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
         }
     }
     pl.a_chunks = (int)pl.chunks.size();
+    /* Both parts alternate between at most two (accumulator, instruction descriptor) pairs -- even entries one, odd
+     * entries the other -- and only the first MMA into an accumulator does not accumulate.  The kernel relies on this
+     * to keep nothing but the two operand offsets per MMA in uniform registers; verify it rather than assume it. */
+    pl.prog_regular = true;
+    for (int w = 0; w < 2; w++)
+        for (size_t i = 0; i < part[w].size(); i++) {
+            const TcMma &m = part[w][i], &ref = part[w][i & 1];
+            const bool first = i == 0 || (i == 1 && (part[w][1].d_acc & 0xffffu) != (part[w][0].d_acc & 0xffffu));
+            if ((m.d_acc & 0xffffu) != (ref.d_acc & 0xffffu) || m.idesc != ref.idesc || (m.d_acc >> 31) != (first ? 0u : 1u))
+                pl.prog_regular = false;
+        }
     pl.prog = part[0];
     pl.prog_split = (int)part[0].size();
     pl.prog.insert(pl.prog.end(), part[1].begin(), part[1].end());
@@ -844,6 +862,7 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     p.n_tiles = b.geom.n_tiles; p.total_tiles = b.geom.total_tiles;
     p.C = pl.C; p.G = pl.G; p.Kp = pl.Kp; p.Q = pl.Q; p.R = pl.R;
     p.nb_stages = pl.nb_stages; p.prog_len = (int)pl.prog.size(); p.prog_split = pl.prog_split;
+    p.prog_regular = pl.prog_regular ? 1 : 0;
     p.inv_nslab = 1.0f / (float)(pl.Kp / 16);
     p.a_group_bytes = (uint32_t)pl.a_group_bytes; p.b_stage_bytes = (uint32_t)pl.b_stage_bytes;
     p.atan = b.atan;

@@ -50,6 +50,7 @@ struct TcPlan {
     int atan_copies = 1;                /* interleaved copies of the arctangent table in shared memory (16 or 1) */
     int rot_lt = 0;                     /* entries per channel of the in-kernel derotator phase table (0 = none) */
     std::vector<TcMma> prog;            /* the MMAs of one tile: [0, prog_split) issued by MMA warp 0, the rest by warp 1 */
+    bool prog_regular = false;          /* (accumulator, descriptor) alternate even/odd within each warp's part: fast issue path */
     int prog_split = 0;                 /* the two warps own disjoint accumulators, so their order does not matter */
     /* tap image construction: for image chunk i, which (q, kk) it covers and which limb/term it holds */
     struct Chunk { int q, kk, term; };
