@@ -450,6 +450,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         auto phase_word = [&](int it) -> int {
             if (!live) return 0;
             const int tile = tile0 + it;
+            if (!table_mode && (long long)TC_OUT * tile + 8 * blk0 >= p.K) return 0;   /* block past the last output: its
+                                                                                          checkpoint was never written */
             if (table_mode) {
                 uint32_t ix = tph;
                 tph += tstep;
