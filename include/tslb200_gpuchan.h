@@ -140,6 +140,15 @@ const char *gpuchan_last_error(void);
 int gpuchan_host_alloc(void **pp, size_t bytes);
 int gpuchan_host_free(void *p);
 
+/* The FM discriminator as an object of its own, for callers written against multifm/fm_demod.h:22-34
+ * (multifm_fm_demod_init / _process / _cleanup; include/compat/fm_demod.h wraps exactly this).  One real-valued int16
+ * PCM sample per complex int16 input sample (fm_demod.c:53-77); the previous input sample is carried from call to
+ * call and starts at (0, 0).  Inside a channel bank the discriminator is fused into the FIR kernel instead. */
+typedef struct gpufm gpufm_t;
+int gpufm_create(gpufm_t **ph, int32_t device, uint32_t max_samples_per_launch, uint32_t flags /* GPUCHAN_F_ATAN_FMA */);
+int gpufm_process(gpufm_t *h, const int16_t *iq_host, size_t n_complex, int16_t *pcm_host);
+int gpufm_destroy(gpufm_t **ph);
+
 /* Instrumentation (bench.py roofline): CUDA events around each launch of the dominant FIR+FM kernel. */
 int gpuchan_timing_enable(gpuchan_t *h, int on);
 int gpuchan_timing_read(gpuchan_t *h, double *total_ms, uint64_t *nr_launches);

@@ -70,6 +70,11 @@ typedef struct gpupager_cfg {
     const int16_t *taps;          /* [nr_taps] Q.14 int16 taps, see gpupager_quantize_taps */
     uint32_t decoder;             /* GPUPAGER_DECODER_* */
     uint32_t reserved;
+    /* Optional channel selection: decoder channel c reads row channel_map[c] of the PCM array it is fed (what
+     * gpuchan_device_pcm returns) and reports that index in its messages.  The reference starts one `decoder` process
+     * per channel and picks the protocol per process (decoder/decoder.c:688-697): a receiver carrying POCSAG and FLEX
+     * channels side by side is two banks with different maps over the same channel-bank PCM.  NULL = rows 0..n-1. */
+    const uint32_t *channel_map;  /* [nr_channels] */
 } gpupager_cfg;
 
 typedef struct gpupager_msg {

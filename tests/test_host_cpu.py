@@ -1,7 +1,8 @@
 """CPU: the host C side (tsl-sdr_b200/host/: JSON config reader, receiver set-up) without a GPU.
 
 The multifm JSON schema is the reference's (multifm/multifm.c:103-156, multifm/receiver.c:133-229):
-merged files, required keys with the reference's error names, the case-sensitive `dBGain` key (the shipped
+merged files, required keys with the reference's error tags (NO-SAMPLE-RATE, NO-CENTER-FREQ, NO-DECIMATION,
+BAD-DECIMATION-FACTOR, BAD-FILTER-TAPS, INSUFF-FILTER-TAPS, MISSING-CHANNELS, CANT-OPEN-FIFO), the case-sensitive `dBGain` key (the shipped
 etc/pocsag_rtlsdr.json spells it `dbGain`, which the reference silently ignores -- so do we), and on a box without an
 sm_100 device the binary fails loudly at bank creation instead of computing anything on the CPU."""
 import json
@@ -52,11 +53,31 @@ def test_usage_and_malformed(cfg):
 @pytest.mark.skipif(not os.path.exists(BIN), reason="host binary not built")
 def test_required_keys_have_the_reference_error_names(cfg):
     base, taps, write = cfg
-    for key, tag in (("sampleRateHz", "MISSING-SAMPLE-RATE"), ("centerFreqHz", "MISSING-CENTER-FREQ"),
-                     ("decimationFactor", "MISSING-DECIMATION")):
+    # multifm/receiver.c:139-184
+    for key, tag in (("sampleRateHz", "NO-SAMPLE-RATE"), ("centerFreqHz", "NO-CENTER-FREQ"),
+                     ("decimationFactor", "NO-DECIMATION"), ("channels", "MISSING-CHANNELS")):
         c = {k: v for k, v in base.items() if k != key}
         rc, out = run(write("c.json", c), write("t.json", taps))
         assert rc == 1 and tag in out, out
+    rc, out = run(write("c.json", dict(base, decimationFactor=0)), write("t.json", taps))
+    assert rc == 1 and "BAD-DECIMATION-FACTOR" in out, out
+    rc, out = run(write("c.json", base))                                # no lpfTaps in any merged file
+    assert rc == 1 and "BAD-FILTER-TAPS" in out, out
+    rc, out = run(write("c.json", base), write("t.json", {"lpfTaps": [1.0]}))
+    assert rc == 1 and "INSUFF-FILTER-TAPS" in out, out
+    rc, out = run(write("c.json", dict(base, nrSampBufs=0)), write("t.json", taps))
+    assert rc == 1 and "BAD-SAMP-BUFS" in out, out
+    rc, out = run(write("c.json", dict(base, sampleRateHz=1200000.5)), write("t.json", taps))   # integers only
+    assert rc == 1 and "NO-SAMPLE-RATE" in out, out
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="host binary not built")
+def test_json_reader_rejects_truncated_and_deep_input(cfg):
+    base, taps, write = cfg
+    rc, out = run(write("bs.json", '{"device": "abc\\'))              # text ends in a lone backslash
+    assert rc == 1 and "MALFORMED-CONFIG" in out and "unterminated string" in out
+    rc, out = run(write("deep.json", "[" * 100000))
+    assert rc == 1 and "MALFORMED-CONFIG" in out and "nesting too deep" in out
 
 
 @pytest.mark.skipif(not os.path.exists(BIN), reason="host binary not built")

@@ -83,6 +83,9 @@ def _declare(L: C.CDLL) -> None:
     L.gpuchan_tc_plan_query.argtypes = [C.POINTER(GpuChanCfg), C.c_uint32, vp, vp, sz, vp, sz]
     L.gpuchan_math_selftest.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, vp]
     L.gpuchan_discard.argtypes = [vp]
+    L.gpufm_create.argtypes = [C.POINTER(vp), C.c_int32, C.c_uint32, C.c_uint32]
+    L.gpufm_process.argtypes = [vp, vp, sz, vp]
+    L.gpufm_destroy.argtypes = [C.POINTER(vp)]
     L.gpuchan_timing_enable.argtypes = [vp, C.c_int]
     L.gpuchan_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
 
@@ -91,7 +94,8 @@ class GpuPagerCfg(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("nr_channels", C.c_uint32), ("device", C.c_int32),
                 ("interpolate", C.c_uint32), ("decimate", C.c_uint32), ("nr_taps", C.c_uint32),
                 ("max_feed_samples", C.c_uint32), ("flags", C.c_uint32), ("dc_pole", C.c_double),
-                ("taps", C.POINTER(C.c_int16)), ("decoder", C.c_uint32), ("reserved", C.c_uint32)]
+                ("taps", C.POINTER(C.c_int16)), ("decoder", C.c_uint32), ("reserved", C.c_uint32),
+                ("channel_map", C.POINTER(C.c_uint32))]
 
 
 class GpuPagerMsg(C.Structure):
@@ -114,7 +118,7 @@ EXPORTS = ["gpuchan_prepare_taps", "gpuchan_derot_increment", "gpuchan_db_to_gai
            "gpuchan_destroy", "gpuchan_submit", "gpuchan_submit_device", "gpuchan_submit_bytes", "gpuchan_sync", "gpuchan_pending",
            "gpuchan_collect", "gpuchan_collect_iq", "gpuchan_device_pcm", "gpuchan_get_taps",
            "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error", "gpuchan_timing_enable", "gpuchan_in_flight", "gpuchan_discard", "gpuchan_host_alloc", "gpuchan_host_free", "gpuchan_tc_selftest", "gpuchan_math_selftest", "gpuchan_tc_plan_query", "gpuchan_debug_stamps", "gpuchan_stream_wait",
-           "gpuchan_timing_read",
+           "gpuchan_timing_read", "gpufm_create", "gpufm_process", "gpufm_destroy",
            "gpupager_quantize_taps", "gpupager_create", "gpupager_destroy", "gpupager_feed_device", "gpupager_feed",
            "gpupager_dispatch", "gpupager_dispatch_flex", "gpupager_poll", "gpupager_collect_pcm", "gpupager_kernel_launches",
            "gpupager_dropped_msgs", "gpupager_last_error",

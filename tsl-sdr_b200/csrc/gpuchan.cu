@@ -417,6 +417,17 @@ __global__ void widen_bytes_kernel(const uchar2 *__restrict__ src, int *__restri
     }
 }
 
+/* The discriminator alone (multifm/fm_demod.c:36-85) over an already filtered int16 IQ stream: output k from
+ * samples k and k - 1 (the one before the first is carried state) */
+__global__ void fm_only_kernel(const int *__restrict__ iq, size_t n, int last_in, const float2 *__restrict__ tab, AtanParams ap,
+                               short *__restrict__ pcm)
+{
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const int cur = iq[k], prev = k ? iq[k - 1] : last_in;
+        pcm[k] = (short)fm_pcm(lo16(cur), hi16(cur), lo16(prev), hi16(prev), tab, ap);
+    }
+}
+
 template <int CPT, int R>
 size_t imad_smem_bytes(int T, int D)
 {
@@ -480,12 +491,7 @@ struct gpuchan {
 
     /* tensor-core engine */
     TcPlan tc;
-    uint8_t *d_tap_img = nullptr, *d_plane_hi[2] = { nullptr, nullptr }, *d_plane_lo[2] = { nullptr, nullptr };
-    int *d_ckpt2 = nullptr;                 /* second checkpoint buffer (pre-stream runs one batch ahead) */
-    cudaStream_t s_pre = nullptr;           /* prepass + carry + deinterleave of batch i+1 overlap the FIR/FM kernel of batch i */
-    cudaEvent_t ev_in = nullptr, ev_pre_done[2] = { nullptr, nullptr }, ev_main_done[2] = { nullptr, nullptr };
-    uint64_t tc_seq = 0;
-    long long plane_rows = 0;
+    uint8_t *d_tap_img = nullptr;
     long long *d_dbg = nullptr;             /* role clock stamps (GPUCHAN_DEBUG_STAMPS=1) */
     int nr_sms = 148;
     int tc_tune = 0;                        /* GPUCHAN_TC_TUNE: kernel experiment switches (tc_engine.cu) */
@@ -575,14 +581,7 @@ static int free_all(gpuchan *h)
     cudaFree(h->d_last[0]); cudaFree(h->d_last[1]);
     cudaFree(h->d_mu); cudaFree(h->d_lambda); cudaFree(h->d_cyc);
     cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_ckpt);
-    cudaFree(h->d_atan); cudaFree(h->d_tap_img); cudaFree(h->d_dbg); cudaFree(h->d_ckpt2);
-    for (int i = 0; i < 2; i++) {
-        cudaFree(h->d_plane_hi[i]); cudaFree(h->d_plane_lo[i]);
-        if (h->ev_pre_done[i]) cudaEventDestroy(h->ev_pre_done[i]);
-        if (h->ev_main_done[i]) cudaEventDestroy(h->ev_main_done[i]);
-    }
-    if (h->ev_in) cudaEventDestroy(h->ev_in);
-    if (h->s_pre) cudaStreamDestroy(h->s_pre);
+    cudaFree(h->d_atan); cudaFree(h->d_tap_img); cudaFree(h->d_dbg);
     for (int i = 0; i < gpuchan::NSLOT; i++) {
         cudaFree(h->d_stage[i]); cudaFree(h->d_stage8[i]); cudaFree(h->d_pcm[i]); cudaFree(h->d_iq[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -700,12 +699,6 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
         tc_build_tap_image(h->tc, h->h_re.data(), h->h_im.data(), img);
         FAIL_TRY(cudaMalloc(&h->d_tap_img, img.size()));
         FAIL_TRY(cudaMemcpy(h->d_tap_img, img.data(), img.size(), cudaMemcpyHostToDevice));
-        FAIL_TRY(cudaStreamCreateWithFlags(&h->s_pre, cudaStreamNonBlocking));
-        FAIL_TRY(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
-        for (int i = 0; i < 2; i++) {
-            FAIL_TRY(cudaEventCreateWithFlags(&h->ev_pre_done[i], cudaEventDisableTiming));
-            FAIL_TRY(cudaEventCreateWithFlags(&h->ev_main_done[i], cudaEventDisableTiming));
-        }
         if (getenv("GPUCHAN_TC_TUNE")) h->tc_tune = atoi(getenv("GPUCHAN_TC_TUNE"));
         if (getenv("GPUCHAN_TC_SLEEP")) sscanf(getenv("GPUCHAN_TC_SLEEP"), "%u,%u,%u", &h->tc_sleep[0], &h->tc_sleep[1], &h->tc_sleep[2]);
         if (getenv("GPUCHAN_DEBUG_STAMPS")) {
@@ -730,7 +723,6 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
     FAIL_TRY(cudaMalloc(&h->d_lambda, C * sizeof(uint32_t)));
     FAIL_TRY(cudaMalloc(&h->d_cyc, (size_t)C * ROT_LMAX * sizeof(int)));
     FAIL_TRY(cudaMalloc(&h->d_ckpt, h->ckpt_tiles * sub * C * sizeof(int)));
-    if (use_tc) FAIL_TRY(cudaMalloc(&h->d_ckpt2, h->ckpt_tiles * sub * C * sizeof(int)));
     FAIL_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     FAIL_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     for (int i = 0; i < gpuchan::NSLOT; i++) {
@@ -788,8 +780,6 @@ template <int CPT, int R>
 static cudaError_t launch_imad(gpuchan *h, const FirFmParams &p, int nr_tiles, cudaStream_t st)
 {
     const size_t smem = imad_smem_bytes<CPT, R>(h->T, h->D);
-    static thread_local int configured_for = -1;
-    (void)configured_for;
     cudaError_t e = cudaFuncSetAttribute(fir_fm_imad_kernel<CPT, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(nr_tiles, (h->C + 32 * CPT - 1) / (32 * CPT));
@@ -819,20 +809,11 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
     in.carry_len = h->carry_len;
     in.total = avail;
 
-    /* The tensor-core engine reads only the byte planes, so everything that touches the raw samples (derotator
-     * checkpoints, carry, deinterleave) runs on a second stream one batch ahead of the FIR/FM kernel. */
-    /* Measured on B200: next to the persistent FIR/FM kernel (1 CTA/SM, 213 KB smem) the pre-kernels only get
-     * ~2 CTAs per SM and become the critical path (step 0.29 -> 0.38 ms), so the second stream stays off. */
-    const bool overlap_pre = false;
-    cudaStream_t pre = (use_tc && overlap_pre) ? h->s_pre : st;
-    const int pb = (int)(h->tc_seq & 1);
-    if (pre != st) {
-        if (in_ready) CUDA_TRY(cudaStreamWaitEvent(pre, in_ready, 0));
-        CUDA_TRY(cudaStreamWaitEvent(pre, h->ev_main_done[pb], 0));     /* planes/checkpoints pb were read two batches ago */
-    } else if (in_ready) {
-        CUDA_TRY(cudaStreamWaitEvent(st, in_ready, 0));
-    }
-    int *ckpt = (use_tc && pb) ? h->d_ckpt2 : h->d_ckpt;
+    /* Everything of one submit runs in order on st.  (A second stream running the derotator prepass one batch ahead
+     * was measured on B200 and lost: next to the persistent FIR/FM kernel the small kernels get ~2 CTAs per SM and
+     * become the critical path, step 0.29 -> 0.38 ms.) */
+    if (in_ready) CUDA_TRY(cudaStreamWaitEvent(st, in_ready, 0));
+    int *ckpt = h->d_ckpt;
 
     CkptGeom cg{};
     TcGeom tg;
@@ -855,16 +836,16 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
             /* nothing to do */
         } else if (steady) {
             dim3 g((h->C + 63) / 64, (nr_tiles + 15) / 16);
-            rot_prepass_table_kernel<<<g, 64, 0, pre>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, cg,
+            rot_prepass_table_kernel<<<g, 64, 0, st>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, cg,
                                                         nr_tiles, ckpt, 0);
             h->launches++;
         } else {
             /* some channel is still in its transient: walk that part sequentially (one thread per channel), fill
              * everything on a tabulated cycle in parallel */
             dim3 g((h->C + 63) / 64, (nr_tiles + 15) / 16);
-            rot_prepass_table_kernel<<<g, 64, 0, pre>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, cg,
+            rot_prepass_table_kernel<<<g, 64, 0, st>>>(h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc, h->k_total, K, cg,
                                                         nr_tiles, ckpt, 1);
-            rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, pre>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
+            rot_prepass_kernel<<<(h->C + 63) / 64, 64, 0, st>>>(h->d_incr, h->d_rot, h->C, h->d_mu, h->d_lambda, h->d_cyc,
                                                                  h->k_total, K, cg, nr_tiles, ckpt, 1);
             h->launches += 2;
         }
@@ -886,13 +867,7 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
         return GPUCHAN_OK;
     };
     const bool carry_in_kernel = use_tc && K > 0;
-    if (use_tc) {
-        if (!carry_in_kernel) { if (int rc = save_carry(pre)) return rc; }
-        if (pre != st) {
-            CUDA_TRY(cudaEventRecord(h->ev_pre_done[pb], pre));
-            CUDA_TRY(cudaStreamWaitEvent(st, h->ev_pre_done[pb], 0));
-        }
-    }
+    if (use_tc && !carry_in_kernel) { if (int rc = save_carry(st)) return rc; }
 
     if (K > 0) {
         cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -938,12 +913,7 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
         h->pp_last ^= 1;
         h->k_total += K;
     }
-    if (use_tc) {
-        CUDA_TRY(cudaEventRecord(h->ev_main_done[pb], st));
-        h->tc_seq++;
-    } else {
-        if (int rc = save_carry(st)) return rc;
-    }
+    if (!use_tc) { if (int rc = save_carry(st)) return rc; }
     h->pp_carry ^= 1;
     h->carry_len = keep > 0 ? keep : 0;
     h->slotK[slot] = (size_t)K;
@@ -1026,7 +996,6 @@ extern "C" int gpuchan_sync(gpuchan_t *h)
     CUDA_TRY(cudaSetDevice(h->device));
     for (int i = 0; i < gpuchan::NSLOT; i++) CUDA_TRY(cudaEventSynchronize(h->ev_done[i]));
     CUDA_TRY(cudaStreamSynchronize(h->s_in));
-    if (h->s_pre) CUDA_TRY(cudaStreamSynchronize(h->s_pre));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->s_out));
     return GPUCHAN_OK;
@@ -1182,5 +1151,83 @@ extern "C" int gpuchan_debug_stamps(gpuchan_t *h, long long *out)
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(out, h->d_dbg, 3 * 32 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return GPUCHAN_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* FM discriminator as an object of its own (multifm/fm_demod.h:22-34)                        */
+/* ------------------------------------------------------------------------------------------ */
+struct gpufm {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    size_t max_samples = 0;
+    int *d_iq = nullptr;
+    short *d_pcm = nullptr;
+    float2 *d_atan = nullptr;
+    AtanParams atan{};
+    int last = 0;                       /* packed previous input sample, (0, 0) at start (fm_demod.c: zeroed state) */
+    int nr_sms = 148;
+};
+
+extern "C" int gpufm_destroy(gpufm_t **ph)
+{
+    if (!ph || !*ph) return set_err(GPUCHAN_E_BADARGS, "null handle");
+    gpufm *h = *ph;
+    cudaSetDevice(h->device);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    cudaFree(h->d_iq); cudaFree(h->d_pcm); cudaFree(h->d_atan);
+    delete h;
+    *ph = nullptr;
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpufm_create(gpufm_t **ph, int32_t device, uint32_t max_samples, uint32_t flags)
+{
+    if (!ph || !max_samples) return set_err(GPUCHAN_E_BADARGS, "bad argument");
+    *ph = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(GPUCHAN_E_NODEVICE, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return set_err(GPUCHAN_E_BADARGS, "bad device ordinal %d", device);
+    CUDA_TRY(cudaSetDevice(device));
+    gpufm *h = new (std::nothrow) gpufm();
+    if (!h) return set_err(GPUCHAN_E_NOMEM, "out of memory");
+    h->device = device; h->max_samples = max_samples;
+    cudaDeviceProp prop{};
+    float2 tab[256];
+    host_atan_table(tab);
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_iq, (size_t)max_samples * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_pcm, (size_t)max_samples * sizeof(short));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_atan, sizeof(tab));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_atan, tab, sizeof(tab), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_err(GPUCHAN_E_CUDA, "gpufm_create: %s", cudaGetErrorString(e));
+        gpufm_destroy(&h);
+        return GPUCHAN_E_CUDA;
+    }
+    h->nr_sms = prop.multiProcessorCount;
+    h->atan.z_small_thr = host_z_small_thr();
+    h->atan.use_fma = (flags & GPUCHAN_F_ATAN_FMA) ? 1 : 0;
+    *ph = h;
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpufm_process(gpufm_t *h, const int16_t *iq_host, size_t n, int16_t *pcm_host)
+{
+    if (!h || !iq_host || !pcm_host || !n) return set_err(GPUCHAN_E_BADARGS, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (size_t done = 0; done < n; ) {
+        const size_t m = std::min(n - done, h->max_samples);
+        CUDA_TRY(cudaMemcpyAsync(h->d_iq, iq_host + 2 * done, m * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        const unsigned blocks = (unsigned)std::min<size_t>((m + 255) / 256, (size_t)h->nr_sms * 8);
+        fm_only_kernel<<<blocks, 256, 0, h->stream>>>(h->d_iq, m, h->last, h->d_atan, h->atan, h->d_pcm);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(pcm_host + done, h->d_pcm, m * sizeof(short), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->last = ((int)iq_host[2 * (done + m) - 2] & 0xffff) | ((int)iq_host[2 * (done + m) - 1] << 16);
+        done += m;
+    }
     return GPUCHAN_OK;
 }

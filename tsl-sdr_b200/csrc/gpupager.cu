@@ -95,6 +95,7 @@ struct PocsagState {
 };
 
 struct MsgSink {
+    const unsigned *chan_id;    /* [C] channel index reported with a message (nullptr = the decoder channel itself) */
     gpupager_msg *msgs;         /* [C][cap] */
     uint32_t *count;            /* [C] */
     unsigned long long *dropped;
@@ -107,13 +108,14 @@ struct InPcm {
     long long carry_pitch, fresh_pitch;
     long long carry_len, total; /* window = carry_len + fresh_len samples, starting at global index base */
     int invert;                 /* decoder -i: fresh samples are negated (int16 wrap); carried ones already were */
+    const unsigned *map;        /* [C] row of `fresh` each decoder channel reads (nullptr = identity); carry rows are per decoder channel */
 };
 
 __device__ __forceinline__ int pcm_at(const InPcm &w, int c, long long i)
 {
     if (i < 0 || i >= w.total) return 0;
     if (i < w.carry_len) return (int)w.carry[(size_t)c * w.carry_pitch + i];
-    const int v = (int)w.fresh[(size_t)c * w.fresh_pitch + (i - w.carry_len)];
+    const int v = (int)w.fresh[(size_t)(w.map ? w.map[c] : (unsigned)c) * w.fresh_pitch + (i - w.carry_len)];
     return w.invert ? (int)(short)(-v) : v;
 }
 
@@ -217,7 +219,7 @@ __device__ void deliver(PocsagState &p, char *alpha, char *numeric, const MsgSin
     const uint32_t slot = sink.count[c];
     if (slot < sink.cap) {
         gpupager_msg *m = sink.msgs + (size_t)c * sink.cap + slot;
-        m->channel = c; m->kind = is_alpha ? GPUPAGER_MSG_ALPHA : GPUPAGER_MSG_NUMERIC;
+        m->channel = sink.chan_id ? sink.chan_id[c] : (unsigned)c; m->kind = is_alpha ? GPUPAGER_MSG_ALPHA : GPUPAGER_MSG_NUMERIC;
         m->baud = p.baud; m->capcode = p.capcode; m->function = p.function;
         m->capcode_hi = 0;
         for (int i = 0; i < 6; i++) m->aux[i] = 0;
@@ -476,7 +478,7 @@ __device__ gpupager_msg *fx_msg(const FlexState &f, const MsgSink &sink, int c, 
     const uint32_t slot = sink.count[c];
     if (slot >= sink.cap) { atomicAdd(sink.dropped, 1ull); return nullptr; }
     gpupager_msg *m = sink.msgs + (size_t)c * sink.cap + slot;
-    m->channel = c; m->kind = kind; m->baud = c_flex_codings[f.coding].baud;
+    m->channel = sink.chan_id ? sink.chan_id[c] : (unsigned)c; m->kind = kind; m->baud = c_flex_codings[f.coding].baud;
     m->capcode = (uint32_t)capcode; m->capcode_hi = (uint32_t)(capcode >> 32);
     m->function = phase; m->len = 0;
     m->aux[0] = f.cycle_id; m->aux[1] = f.frame_id; m->aux[2] = m->aux[3] = m->aux[4] = m->aux[5] = 0;
@@ -873,7 +875,7 @@ struct gpupager {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_own = nullptr, ev_ext = nullptr;
-    int C = 0;
+    int C = 0, nr_src = 0;
     unsigned interp = 1, decim = 1;
     int M = 0;                          /* taps per phase */
     uint32_t flags = 0;
@@ -899,6 +901,7 @@ struct gpupager {
     gpupager_msg *d_msgs = nullptr;
     uint32_t *d_count = nullptr;
     unsigned long long *d_dropped = nullptr;
+    unsigned *d_map = nullptr;          /* [C] source row per decoder channel (cfg.channel_map), nullptr = identity */
     std::vector<gpupager_msg> queue;    /* decoded, not yet handed out */
     uint64_t launches = 0, dropped = 0;
 };
@@ -909,6 +912,7 @@ static void pager_free(gpupager *h)
     cudaSetDevice(h->device);
     cudaFree(h->d_phase); cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_stage); cudaFree(h->d_res);
     cudaFree(h->d_states); cudaFree(h->d_fstates); cudaFree(h->d_text); cudaFree(h->d_msgs); cudaFree(h->d_count); cudaFree(h->d_dropped);
+    cudaFree(h->d_map);
     if (h->ev_own) cudaEventDestroy(h->ev_own);
     if (h->ev_ext) cudaEventDestroy(h->ev_ext);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -954,6 +958,10 @@ extern "C" int gpupager_create(gpupager_t **ph, const gpupager_cfg *cfg)
     PFAIL(cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming));
 
     const int C = h->C;
+    if (cfg->channel_map) {
+        PFAIL(cudaMalloc(&h->d_map, C * sizeof(unsigned)));
+        PFAIL(cudaMemcpy(h->d_map, cfg->channel_map, C * sizeof(unsigned), cudaMemcpyHostToDevice));
+    }
     size_t max_out = h->max_feed;
     if (!bypass) {
         h->interp = cfg->interpolate; h->decim = cfg->decimate;
@@ -971,7 +979,9 @@ extern "C" int gpupager_create(gpupager_t **ph, const gpupager_cfg *cfg)
     }
     h->res_pitch = (long long)((max_out + 63) & ~(size_t)63);
     PFAIL(cudaMalloc(&h->d_res, (size_t)C * h->res_pitch * sizeof(short)));
-    PFAIL(cudaMalloc(&h->d_stage, (size_t)C * h->max_feed * sizeof(short)));
+    h->nr_src = C;                      /* rows a host feed carries: every row the map refers to */
+    if (cfg->channel_map) for (int c = 0; c < C; c++) if ((int)cfg->channel_map[c] + 1 > h->nr_src) h->nr_src = (int)cfg->channel_map[c] + 1;
+    PFAIL(cudaMalloc(&h->d_stage, (size_t)h->nr_src * h->max_feed * sizeof(short)));
     if (h->decoder == GPUPAGER_DECODER_FLEX) {
         PFAIL(cudaMalloc(&h->d_fstates, (size_t)C * sizeof(FlexState)));
         PFAIL(cudaMemset(h->d_fstates, 0, (size_t)C * sizeof(FlexState)));
@@ -1027,6 +1037,7 @@ static int pager_run(gpupager *h, const short *d_pcm, size_t pitch, size_t n, cu
         in.carry_pitch = h->carry_pitch; in.fresh_pitch = (long long)pitch;
         in.carry_len = h->carry_len; in.total = h->carry_len + (long long)n;
         in.invert = (h->flags & GPUPAGER_F_INVERT) ? 1 : 0;
+        in.map = h->d_map;
         const unsigned long long total = h->total_in + n;
         /* outputs m with n_m + M < total  <=>  m < (total - M) * I / D   (polyphase_fir.c:184, strict) */
         unsigned long long m_end = h->m_next;
@@ -1062,12 +1073,13 @@ static int pager_run(gpupager *h, const short *d_pcm, size_t pitch, size_t n, cu
         h->carry_len = keep;
         h->in_base = n_next;
         dec_in = h->d_res; dec_pitch = h->res_pitch; nr_dec = (unsigned)nr_out;
-    } else if (h->flags & GPUPAGER_F_INVERT) {
-        /* no resampler to fold the negation into: a negated copy */
+    } else if ((h->flags & GPUPAGER_F_INVERT) || h->d_map) {
+        /* no resampler to fold the negation / the channel selection into: a (negated, gathered) copy */
         if (n > (size_t)h->res_pitch) return perr(GPUPAGER_E_INVAL, "feed too large");
         InPcm in;
         in.carry = nullptr; in.fresh = d_pcm; in.carry_pitch = 0; in.fresh_pitch = (long long)pitch;
-        in.carry_len = 0; in.total = (long long)n; in.invert = 1;
+        in.carry_len = 0; in.total = (long long)n; in.invert = (h->flags & GPUPAGER_F_INVERT) ? 1 : 0;
+        in.map = h->d_map;
         dim3 grid((unsigned)((n + 255) / 256), C);
         pcm_carry_kernel<<<grid, 256, 0, st>>>(in, 0, h->d_res, h->res_pitch, (int)n);
         h->launches++;
@@ -1082,7 +1094,7 @@ static int pager_run(gpupager *h, const short *d_pcm, size_t pitch, size_t n, cu
     }
     h->last_out = nr_dec;
     if (nr_dec) {
-        MsgSink sink{ h->d_msgs, h->d_count, h->d_dropped, h->msg_cap };
+        MsgSink sink{ h->d_map, h->d_msgs, h->d_count, h->d_dropped, h->msg_cap };
         if (h->decoder == GPUPAGER_DECODER_FLEX)
             flex_kernel<<<(C + 31) / 32, 32, 0, st>>>(h->d_fstates, C, const_cast<short *>(dec_in), dec_pitch, nr_dec, sink,
                                                       (h->flags & GPUPAGER_F_DC_BLOCK) ? 1 : 0, h->dc_p);
@@ -1121,7 +1133,7 @@ extern "C" int gpupager_feed(gpupager_t *h, const int16_t *pcm_host, size_t pitc
     if (n == 0) return GPUPAGER_OK;
     PCUDA(cudaSetDevice(h->device));
     PCUDA(cudaMemcpy2DAsync(h->d_stage, h->max_feed * sizeof(short), pcm_host, pitch * sizeof(short), n * sizeof(short),
-                            h->C, cudaMemcpyHostToDevice, h->stream));
+                            h->nr_src, cudaMemcpyHostToDevice, h->stream));
     return pager_run(h, h->d_stage, h->max_feed, n, h->stream);
 }
 

@@ -33,7 +33,7 @@ def quantize_taps(coeffs):
 
 class GpuPager:
     def __init__(self, nr_channels, max_feed_samples, taps_q14=None, interpolate=1, decimate=1, device=0, flags=0,
-                 dc_pole=0.9999, decoder=DECODER_POCSAG):
+                 dc_pole=0.9999, decoder=DECODER_POCSAG, channel_map=None):
         L = self._L = _lib.lib()
         cfg = _lib.GpuPagerCfg()
         cfg.struct_size = C.sizeof(_lib.GpuPagerCfg)
@@ -48,6 +48,10 @@ class GpuPager:
         cfg.dc_pole = float(dc_pole)
         cfg.taps = None if self._taps is None else self._taps.ctypes.data_as(C.POINTER(C.c_int16))
         cfg.decoder = int(decoder)
+        self._map = None if channel_map is None else np.ascontiguousarray(channel_map, dtype=np.uint32)
+        if self._map is not None:
+            assert len(self._map) == int(nr_channels)
+            cfg.channel_map = self._map.ctypes.data_as(C.POINTER(C.c_uint32))
         self._h = C.c_void_p()
         _check(L.gpupager_create(C.byref(self._h), C.byref(cfg)), "gpupager_create")
         self.nr_channels = int(nr_channels)
@@ -64,7 +68,8 @@ class GpuPager:
 
     def feed(self, pcm: np.ndarray):
         """pcm: [nr_channels, n] int16 in host memory."""
-        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.nr_channels
+        rows = self.nr_channels if self._map is None else int(self._map.max()) + 1
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] >= rows
         pcm = np.ascontiguousarray(pcm)
         _check(self._L.gpupager_feed(self._h, pcm.ctypes.data, pcm.shape[1], pcm.shape[1]), "gpupager_feed")
 

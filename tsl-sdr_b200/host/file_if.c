@@ -59,8 +59,7 @@ static aresult_t file_worker_thread_work(struct receiver *rx)
             if (nr > 0) sbuf->nr_samples = (uint32_t)(nr / 2);
         }
         if (nr <= 0 || sbuf->nr_samples == 0) {     /* EOF: the reference aborts here (receiver.c:84) */
-            sbuf->refcount = 1;                     /* never delivered: hand it back to the pool ourselves */
-            sample_buf_decref(sbuf);
+            sample_buf_decref(sbuf);                /* never delivered: our reference (set by alloc) returns it to the pool */
             break;
         }
         receiver_sample_buf_deliver(rx, sbuf);
@@ -73,6 +72,7 @@ static aresult_t file_cleanup(struct receiver *rx)
     struct file_worker_thread *thr = (struct file_worker_thread *)rx;
     if (thr->fd >= 0) close(thr->fd);
     free(thr->bounce);
+    free(thr);              /* receiver_cleanup calls this last: the receiver lives inside thr */
     return A_OK;
 }
 
@@ -85,6 +85,7 @@ aresult_t file_worker_thread_new(struct receiver **pthr, const jnode *cfg)
     if (!dev || json_get_string(dev, "filename", &fname)) { B200_MSG("E", "MISSING-FILENAME", "device.filename is required"); return A_E_INVAL; }
     if (json_get_string(dev, "fileFormat", &fmt)) fmt = "cs16";
     struct file_worker_thread *thr = calloc(1, sizeof(*thr));
+    if (!thr) return A_E_NOMEM;
     if (!strcmp(fmt, "cs16")) thr->fmt = FMT_CS16;
     else if (!strcmp(fmt, "cs8")) thr->fmt = FMT_CS8;
     else if (!strcmp(fmt, "cu8")) thr->fmt = FMT_CU8;
@@ -92,6 +93,7 @@ aresult_t file_worker_thread_new(struct receiver **pthr, const jnode *cfg)
     thr->fd = open(fname, O_RDONLY);
     if (thr->fd < 0) { B200_MSG("E", "BAD-FILE", "cannot open %s: %s", fname, strerror(errno)); free(thr); return A_E_INVAL; }
     thr->bounce = malloc(SAMPLES_PER_BUF * 2);
+    if (!thr->bounce) { close(thr->fd); free(thr); return A_E_NOMEM; }
     aresult_t ret = receiver_init(&thr->rx, cfg, file_worker_thread_work, file_cleanup, SAMPLES_PER_BUF);
     if (FAILED(ret)) { close(thr->fd); free(thr->bounce); free(thr); return ret; }
     *pthr = &thr->rx;

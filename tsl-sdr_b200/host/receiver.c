@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -41,6 +42,7 @@ aresult_t receiver_sample_buf_alloc(struct receiver *rx, struct sample_buf **pbu
     b->release = _sample_buf_release;
     b->priv = rx;
     b->nr_samples = 0;
+    atomic_store((_Atomic uint32_t *)&b->refcount, 1);      /* the source owns it until it is delivered */
     *pbuf = b;
     return A_OK;
 }
@@ -49,11 +51,16 @@ aresult_t receiver_sample_buf_alloc(struct receiver *rx, struct sample_buf **pbu
 aresult_t receiver_sample_buf_deliver(struct receiver *rx, struct sample_buf *buf)
 {
     if (!rx || !buf) return A_E_BADARGS;
-    if (0 == buf->nr_samples) { sample_buf_decref(buf); return A_E_INVAL; }
     atomic_store((_Atomic uint32_t *)&buf->refcount, 1);
+    if (0 == buf->nr_samples) { sample_buf_decref(buf); return A_E_INVAL; }     /* back to the pool, nothing queued */
     pthread_mutex_lock(&rx->q_mtx);
     while (((rx->q_head + 1) & 127) == rx->q_tail && rx->running)     /* queue full: back-pressure the file source */
         pthread_cond_wait(&rx->q_cv, &rx->q_mtx);
+    if (((rx->q_head + 1) & 127) == rx->q_tail) {                     /* still full: the receiver stopped -- drop, never overwrite */
+        pthread_mutex_unlock(&rx->q_mtx);
+        sample_buf_decref(buf);
+        return A_E_BUSY;
+    }
     rx->queue[rx->q_head] = buf;
     rx->q_head = (rx->q_head + 1) & 127;
     pthread_mutex_unlock(&rx->q_mtx);
@@ -291,16 +298,22 @@ aresult_t receiver_init(struct receiver *rx, const jnode *cfg, receiver_rx_threa
 
     int v = 0;
     rx->nr_samp_bufs = 64;                                                     /* receiver.c:133 default */
+    /* tags and texts of multifm/receiver.c:133-184 */
     if (!json_get_int(cfg, "nrSampBufs", &v)) rx->nr_samp_bufs = v;
-    if (json_get_int(cfg, "sampleRateHz", &v) || v <= 0) { B200_MSG("E", "MISSING-SAMPLE-RATE", "Need to specify 'sampleRateHz' in configuration."); return A_E_INVAL; }
+    else B200_MSG("I", "DEFAULT-SAMP-BUFS", "Setting sample buffer count to 64");
+    if (rx->nr_samp_bufs <= 0) { B200_MSG("E", "BAD-SAMP-BUFS", "nrSampBufs of '%d' is not valid.", rx->nr_samp_bufs); return A_E_INVAL; }
+    if (json_get_int(cfg, "sampleRateHz", &v)) { B200_MSG("I", "NO-SAMPLE-RATE", "Need to specify a sample rate, in Hertz."); return A_E_INVAL; }
+    if (v <= 0) { B200_MSG("E", "BAD-SAMPLE-RATE", "Sample rate of '%d' is not valid.", v); return A_E_INVAL; }
     rx->sample_rate_hz = (uint32_t)v;
-    if (json_get_int(cfg, "centerFreqHz", &v)) { B200_MSG("E", "MISSING-CENTER-FREQ", "Need to specify 'centerFreqHz' in configuration."); return A_E_INVAL; }
-    rx->center_freq_hz = (uint32_t)v;
-    if (json_get_int(cfg, "decimationFactor", &v) || v <= 0) { B200_MSG("E", "MISSING-DECIMATION", "Need to specify 'decimationFactor' in configuration."); return A_E_INVAL; }
+    if (json_get_int(cfg, "centerFreqHz", &v)) { B200_MSG("I", "NO-CENTER-FREQ", "You forgot to specify a center frequency, in Hz."); return A_E_INVAL; }
+    rx->center_freq_hz = (uint32_t)v;       /* a 64-bit JSON integer wrapped into an int, like the reference (json_get_int) */
+    if (json_get_int(cfg, "decimationFactor", &v)) { B200_MSG("I", "NO-DECIMATION", "Not decimating the output signal: using full bandwidth."); return A_E_INVAL; }
+    if (v <= 0) { B200_MSG("E", "BAD-DECIMATION-FACTOR", "Decimation factor of '%d' is not valid.", v); return A_E_INVAL; }
     rx->decimation = (uint32_t)v;
 
     const jnode *taps = json_get(cfg, "lpfTaps");
-    if (!taps || taps->type != J_ARR || taps->len < 2) { B200_MSG("E", "BAD-FILTER-TAPS", "Need to provide a baseband filter with at least two filter taps as 'lpfTaps'."); return A_E_INVAL; }
+    if (!taps || taps->type != J_ARR) { B200_MSG("E", "BAD-FILTER-TAPS", "Need to provide a baseband filter with at least two filter taps as 'lpfTaps'."); return A_E_INVAL; }
+    if (taps->len <= 1) { B200_MSG("E", "INSUFF-FILTER-TAPS", "Not enough filter taps for the low-pass filter."); return A_E_INVAL; }
     rx->nr_lpf_taps = taps->len;
     rx->lpf_taps = calloc(taps->len, sizeof(double));
     for (size_t i = 0; i < taps->len; i++) {
@@ -309,7 +322,7 @@ aresult_t receiver_init(struct receiver *rx, const jnode *cfg, receiver_rx_threa
     }
 
     const jnode *chans = json_get(cfg, "channels");
-    if (!chans || chans->type != J_ARR || chans->len == 0) { B200_MSG("E", "MISSING-CHANNELS", "Need to specify an array of 'channels'."); return A_E_INVAL; }
+    if (!chans || chans->type != J_ARR || chans->len == 0) { B200_MSG("E", "MISSING-CHANNELS", "Need to specify at least one channel to demodulate."); return A_E_INVAL; }
     rx->nr_demod_threads = chans->len;
     rx->channels = calloc(chans->len, sizeof(*rx->channels));
     bool any_debug = false;
@@ -348,7 +361,8 @@ aresult_t receiver_init(struct receiver *rx, const jnode *cfg, receiver_rx_threa
     int32_t *offs = calloc(C, sizeof(int32_t));
     double *gains = calloc(C, sizeof(double));
     for (size_t i = 0; i < C; i++) {
-        offs[i] = (int32_t)rx->channels[i].center_freq_hz - (int32_t)rx->center_freq_hz;    /* receiver.c:229 */
+        /* receiver.c:229: (int32_t)nb_center_freq - center_freq on wrapped ints -- correct modulo 2^32 even above 2^31 Hz */
+        offs[i] = (int32_t)((uint32_t)rx->channels[i].center_freq_hz - rx->center_freq_hz);
         gains[i] = rx->channels[i].gain;
     }
     gpuchan_cfg gc;
@@ -408,17 +422,22 @@ aresult_t receiver_init(struct receiver *rx, const jnode *cfg, receiver_rx_threa
         }
     }
 
-    /* open outputs last: a FIFO open blocks until a reader appears (multifm/demod.c:323,331) */
+    /* open outputs last: a FIFO open blocks until a reader appears.  multifm/demod.c:323,331: O_WRONLY only -- the
+     * FIFO (or file) must exist, a mistyped path is an error, nothing is created.  A regular file is emptied first so
+     * that a rerun never leaves stale PCM behind the new data. */
     signal(SIGPIPE, SIG_IGN);
     for (size_t i = 0; i < C; i++) {
         struct receiver_channel *ch = &rx->channels[i];
-        if (ch->signal_debug) {
-            ch->debug_fd = open(ch->signal_debug, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-            if (ch->debug_fd < 0) { B200_MSG("E", "BAD-DEBUG-FILE", "%s: %s", ch->signal_debug, strerror(errno)); return A_E_INVAL; }
+        struct stat sb;
+        if (ch->signal_debug && *ch->signal_debug) {
+            ch->debug_fd = open(ch->signal_debug, O_WRONLY);
+            if (ch->debug_fd < 0) { B200_MSG("F", "CANT-OPEN-SIGNAL-DEBUG", "Unable to open signal debug dump file '%s'", ch->signal_debug); return A_E_INVAL; }
+            if (0 == fstat(ch->debug_fd, &sb) && S_ISREG(sb.st_mode) && ftruncate(ch->debug_fd, 0)) { /* keep going */ }
         }
         if (strcmp(ch->out_fifo, "/dev/null") == 0 && rx->pager) continue;     /* decode-only channel */
-        ch->fifo_fd = open(ch->out_fifo, O_WRONLY | O_CREAT, 0644);
-        if (ch->fifo_fd < 0) { B200_MSG("E", "BAD-FIFO", "Bad FIFO path %s: %s", ch->out_fifo, strerror(errno)); return A_E_INVAL; }
+        ch->fifo_fd = open(ch->out_fifo, O_WRONLY);
+        if (ch->fifo_fd < 0) { B200_MSG("F", "CANT-OPEN-FIFO", "Unable to open output fifo '%s'", ch->out_fifo); return A_E_INVAL; }
+        if (0 == fstat(ch->fifo_fd, &sb) && S_ISREG(sb.st_mode) && ftruncate(ch->fifo_fd, 0)) { /* keep going */ }
     }
     return A_OK;
 }
@@ -459,7 +478,6 @@ aresult_t receiver_cleanup(struct receiver **prx)
         pthread_join(rx->rx_thread, NULL);
         pthread_join(rx->consumer_thread, NULL);
     }
-    if (rx->cleanup_func) rx->cleanup_func(rx);
     for (size_t i = 0; i < rx->nr_demod_threads; i++) {
         struct receiver_channel *ch = &rx->channels[i];
         if (ch->fifo_fd >= 0) close(ch->fifo_fd);
@@ -473,6 +491,9 @@ aresult_t receiver_cleanup(struct receiver **prx)
     if (rx->msg_out && rx->msg_out != stdout) fclose(rx->msg_out);
     for (int i = 0; i < rx->nr_samp_bufs; i++) free(rx->pool[i]);   /* all buffers are back in the pool by now */
     free(rx->pool); free(rx->channels); free(rx->lpf_taps);
+    pthread_mutex_destroy(&rx->pool_mtx); pthread_mutex_destroy(&rx->q_mtx); pthread_cond_destroy(&rx->q_cv);
+    /* the source goes last: its cleanup releases the object that embeds this receiver (file_worker_thread) */
+    if (rx->cleanup_func) rx->cleanup_func(rx);
     *prx = NULL;
     return A_OK;
 }
