@@ -117,6 +117,10 @@ int gpuchan_pending(gpuchan_t *h, size_t *n_per_channel);
 /* Copy the oldest uncollected batch's PCM to host: channel c occupies pcm_host[c*cap_per_channel ... + n).
  * Blocks until the data has arrived, then retires the batch. */
 int gpuchan_collect(gpuchan_t *h, int16_t *pcm_host, size_t cap_per_channel, size_t *n_per_channel);
+/* The same in two halves: _begin enqueues the copy-out of the oldest batch (asynchronous), _end waits for it and retires the
+ * batch.  Lets a caller with several banks (gpuchan_multi_collect) run all copy-outs side by side. */
+int gpuchan_collect_begin(gpuchan_t *h, int16_t *pcm_host, size_t cap_per_channel);
+int gpuchan_collect_end(gpuchan_t *h, size_t *n_per_channel);
 /* Post-FIR IQ tap (2 int16 per output) of the batch most recently returned by gpuchan_collect;
  * needs GPUCHAN_F_KEEP_IQ and must be called before that batch's slot is reused (two submits later). */
 int gpuchan_collect_iq(gpuchan_t *h, int16_t *iq_host, size_t cap_per_channel, size_t *n_per_channel);
@@ -140,6 +144,25 @@ const char *gpuchan_last_error(void);
 int gpuchan_host_alloc(void **pp, size_t bytes);
 int gpuchan_host_free(void *p);
 
+/* ---- one process, several GPUs ---------------------------------------------------------------------------------
+ * The channels of ONE configuration sharded over N devices (contiguous channel ranges, sizes differing by at most
+ * one), every batch delivered to all of them: receiver_sample_buf_deliver's fan-out (multifm/receiver.c:78-98) across
+ * devices.  cfg describes ALL channels (cfg->device is ignored).  PCM comes back in the configuration's channel
+ * order.  Same stream contract and the same two-batches-in-flight rule as a single bank. */
+#define GPUCHAN_FANOUT_HOST   0     /* every GPU copies the (pinned) host batch over its own PCIe link */
+#define GPUCHAN_FANOUT_RELAY  1     /* the batch enters devices[0]; NVLink relay chain on the copy engines (tslb200_gpurelay.h) */
+typedef struct gpuchan_multi gpuchan_multi_t;
+int gpuchan_multi_create(gpuchan_multi_t **ph, const gpuchan_cfg *cfg, const int32_t *devices, uint32_t nr_devices, uint32_t fanout);
+int gpuchan_multi_destroy(gpuchan_multi_t **ph);
+int gpuchan_multi_submit(gpuchan_multi_t *h, const int16_t *iq_host, size_t n_complex);
+int gpuchan_multi_pending(gpuchan_multi_t *h, size_t *n_per_channel);
+int gpuchan_multi_collect(gpuchan_multi_t *h, int16_t *pcm_host, size_t cap_per_channel, size_t *n_per_channel);
+int gpuchan_multi_discard(gpuchan_multi_t *h);
+int gpuchan_multi_sync(gpuchan_multi_t *h);
+uint32_t gpuchan_multi_devices(gpuchan_multi_t *h);
+/* the bank of device i and the channel range it owns (for chaining per-device pager banks on gpuchan_device_pcm) */
+int gpuchan_multi_bank(gpuchan_multi_t *h, uint32_t i, gpuchan_t **bank, uint32_t *first_channel, uint32_t *nr_channels);
+
 /* The FM discriminator as an object of its own, for callers written against multifm/fm_demod.h:22-34
  * (multifm_fm_demod_init / _process / _cleanup; include/compat/fm_demod.h wraps exactly this).  One real-valued int16
  * PCM sample per complex int16 input sample (fm_demod.c:53-77); the previous input sample is carried from call to
@@ -152,6 +175,10 @@ int gpufm_destroy(gpufm_t **ph);
 /* Instrumentation (bench.py roofline): CUDA events around each launch of the dominant FIR+FM kernel. */
 int gpuchan_timing_enable(gpuchan_t *h, int on);
 int gpuchan_timing_read(gpuchan_t *h, double *total_ms, uint64_t *nr_launches);
+
+/* Tensor-core work of one launch, for the MAC/s roofline: out = { tcgen05.mma (M = 128, K = 32 int8) instructions per
+ * tile, their N, PCM outputs per channel per tile, channel groups }; zeros on the IMAD engine. */
+int gpuchan_tc_model(gpuchan_t *h, uint64_t out[4]);
 
 /* Diagnostics (GPUCHAN_DEBUG_STAMPS=1 at create): clock64 stamps of CTA 0's roles, out = [3][32][8] int64. */
 int gpuchan_debug_stamps(gpuchan_t *h, long long *out);

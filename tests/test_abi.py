@@ -14,7 +14,7 @@ def declared_symbols():
     syms = set()
     for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
         txt = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
-        syms |= set(re.findall(r"\b((?:gpuchan|gpupager|gpumm|gpufm|tslb200)_\w+)\s*\(", txt))
+        syms |= set(re.findall(r"\b((?:gpuchan|gpupager|gpumm|gpufm|gpurelay|tslb200)_\w+)\s*\(", txt))
     return syms
 
 

@@ -83,11 +83,42 @@ def _declare(L: C.CDLL) -> None:
     L.gpuchan_tc_plan_query.argtypes = [C.POINTER(GpuChanCfg), C.c_uint32, vp, vp, sz, vp, sz]
     L.gpuchan_math_selftest.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, vp]
     L.gpuchan_discard.argtypes = [vp]
+    L.gpuchan_tc_model.argtypes = [vp, vp]
+    L.gpuchan_collect_begin.argtypes = [vp, vp, sz]
+    L.gpuchan_collect_end.argtypes = [vp, C.POINTER(sz)]
+    L.gpuchan_multi_create.argtypes = [C.POINTER(vp), C.POINTER(GpuChanCfg), vp, C.c_uint32, C.c_uint32]
+    L.gpuchan_multi_destroy.argtypes = [C.POINTER(vp)]
+    L.gpuchan_multi_submit.argtypes = [vp, vp, sz]
+    L.gpuchan_multi_pending.argtypes = [vp, C.POINTER(sz)]
+    L.gpuchan_multi_collect.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.gpuchan_multi_discard.argtypes = [vp]
+    L.gpuchan_multi_sync.argtypes = [vp]
+    L.gpuchan_multi_devices.restype = C.c_uint32
+    L.gpuchan_multi_devices.argtypes = [vp]
+    L.gpuchan_multi_bank.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.gpurelay_flags_bytes.restype = sz
+    L.gpurelay_flags_bytes.argtypes = [C.c_uint32, C.c_uint32]
+    L.gpurelay_create.argtypes = [C.POINTER(vp), C.POINTER(GpuRelayCfg)]
+    L.gpurelay_destroy.argtypes = [C.POINTER(vp)]
+    L.gpurelay_slot.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
+    L.gpurelay_export.argtypes = [vp, vp]
+    L.gpurelay_connect_ipc.argtypes = [vp, vp]
+    L.gpurelay_connect_local.argtypes = [vp, vp]
+    L.gpurelay_acquire.argtypes = [vp, C.c_uint64, vp]
+    L.gpurelay_advance.argtypes = [vp, C.c_uint64, sz, vp, C.POINTER(vp)]
+    L.gpurelay_release.argtypes = [vp, C.c_uint64, vp]
+    L.gpurelay_last_error.restype = C.c_char_p
     L.gpufm_create.argtypes = [C.POINTER(vp), C.c_int32, C.c_uint32, C.c_uint32]
     L.gpufm_process.argtypes = [vp, vp, sz, vp]
     L.gpufm_destroy.argtypes = [C.POINTER(vp)]
     L.gpuchan_timing_enable.argtypes = [vp, C.c_int]
     L.gpuchan_timing_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+
+
+class GpuRelayCfg(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32), ("nr_slots", C.c_uint32),
+                ("device", C.c_int32), ("reserved", C.c_uint32), ("slot_bytes", C.c_uint64), ("shm_name", C.c_char_p),
+                ("flags_host", C.c_void_p)]
 
 
 class GpuPagerCfg(C.Structure):
@@ -118,7 +149,11 @@ EXPORTS = ["gpuchan_prepare_taps", "gpuchan_derot_increment", "gpuchan_db_to_gai
            "gpuchan_destroy", "gpuchan_submit", "gpuchan_submit_device", "gpuchan_submit_bytes", "gpuchan_sync", "gpuchan_pending",
            "gpuchan_collect", "gpuchan_collect_iq", "gpuchan_device_pcm", "gpuchan_get_taps",
            "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error", "gpuchan_timing_enable", "gpuchan_in_flight", "gpuchan_discard", "gpuchan_host_alloc", "gpuchan_host_free", "gpuchan_tc_selftest", "gpuchan_math_selftest", "gpuchan_tc_plan_query", "gpuchan_debug_stamps", "gpuchan_stream_wait",
-           "gpuchan_timing_read", "gpufm_create", "gpufm_process", "gpufm_destroy",
+           "gpuchan_timing_read", "gpuchan_tc_model", "gpuchan_collect_begin", "gpuchan_collect_end",
+           "gpuchan_multi_create", "gpuchan_multi_destroy", "gpuchan_multi_submit", "gpuchan_multi_pending", "gpuchan_multi_collect",
+           "gpuchan_multi_discard", "gpuchan_multi_sync", "gpuchan_multi_devices", "gpuchan_multi_bank",
+           "gpurelay_flags_bytes", "gpurelay_create", "gpurelay_destroy", "gpurelay_slot", "gpurelay_export", "gpurelay_connect_ipc",
+           "gpurelay_connect_local", "gpurelay_acquire", "gpurelay_advance", "gpurelay_release", "gpurelay_last_error", "gpufm_create", "gpufm_process", "gpufm_destroy",
            "gpupager_quantize_taps", "gpupager_create", "gpupager_destroy", "gpupager_feed_device", "gpupager_feed",
            "gpupager_dispatch", "gpupager_dispatch_flex", "gpupager_poll", "gpupager_collect_pcm", "gpupager_kernel_launches",
            "gpupager_dropped_msgs", "gpupager_last_error",

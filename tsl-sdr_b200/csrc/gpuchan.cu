@@ -1020,10 +1020,10 @@ extern "C" int gpuchan_discard(gpuchan_t *h)
     return GPUCHAN_OK;
 }
 
-extern "C" int gpuchan_collect(gpuchan_t *h, int16_t *pcm_host, size_t cap, size_t *n)
+/* copy-out of the oldest batch, split so that several banks (gpuchan_multi) can run theirs side by side */
+extern "C" int gpuchan_collect_begin(gpuchan_t *h, int16_t *pcm_host, size_t cap)
 {
-    if (!h || !pcm_host || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
-    *n = 0;
+    if (!h || !pcm_host) return set_err(GPUCHAN_E_BADARGS, "null argument");
     if (h->collect_seq >= h->submit_seq) return GPUCHAN_OK;          /* nothing in flight */
     const int slot = (int)(h->collect_seq % gpuchan::NSLOT);
     const size_t K = h->slotK[slot];
@@ -1033,11 +1033,29 @@ extern "C" int gpuchan_collect(gpuchan_t *h, int16_t *pcm_host, size_t cap, size
     if (K)
         CUDA_TRY(cudaMemcpy2DAsync(pcm_host, cap * sizeof(int16_t), h->d_pcm[slot], h->pitch * sizeof(int16_t),
                                    K * sizeof(int16_t), h->C, cudaMemcpyDeviceToHost, h->s_out));
+    return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_collect_end(gpuchan_t *h, size_t *n)
+{
+    if (!h || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    *n = 0;
+    if (h->collect_seq >= h->submit_seq) return GPUCHAN_OK;
+    const int slot = (int)(h->collect_seq % gpuchan::NSLOT);
+    CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaStreamSynchronize(h->s_out));
-    *n = K;
+    *n = h->slotK[slot];
     h->collected_slot = slot;
     h->collect_seq++;
     return GPUCHAN_OK;
+}
+
+extern "C" int gpuchan_collect(gpuchan_t *h, int16_t *pcm_host, size_t cap, size_t *n)
+{
+    if (!h || !pcm_host || !n) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    *n = 0;
+    if (int rc = gpuchan_collect_begin(h, pcm_host, cap)) return rc;
+    return gpuchan_collect_end(h, n);
 }
 
 extern "C" int gpuchan_collect_iq(gpuchan_t *h, int16_t *iq_host, size_t cap, size_t *n)
@@ -1125,6 +1143,18 @@ extern "C" int gpuchan_timing_read(gpuchan_t *h, double *total_ms, uint64_t *nr_
     }
     h->timed.clear();
     *total_ms = sum; *nr_launches = n;
+    return GPUCHAN_OK;
+}
+
+/* What one launch of the dominant kernel issues to the tensor cores (bench.py's MAC/s roofline): out = { tcgen05.mma
+ * instructions per tile, N of one instruction (M = 128, K = 32 int8), PCM outputs per channel a tile produces, channel
+ * groups (CTAs working on the same samples) }.  All zero on the IMAD engine. */
+extern "C" int gpuchan_tc_model(gpuchan_t *h, uint64_t out[4])
+{
+    if (!h || !out) return set_err(GPUCHAN_E_BADARGS, "null argument");
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (h->engine != GPUCHAN_ENGINE_TC) return GPUCHAN_OK;
+    out[0] = h->tc.prog.size(); out[1] = TC_N; out[2] = TC_OUT; out[3] = (uint64_t)h->tc.G;
     return GPUCHAN_OK;
 }
 

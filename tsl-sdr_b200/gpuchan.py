@@ -178,9 +178,85 @@ class GpuChan:
         _check(self._L.gpuchan_timing_read(self._h, C.byref(ms), C.byref(n)), "gpuchan_timing_read")
         return ms.value, n.value
 
+    def tc_model(self):
+        """(MMAs per tile, N per MMA, outputs per tile, channel groups) of the tensor-core engine; zeros on IMAD."""
+        out = (C.c_uint64 * 4)()
+        _check(self._L.gpuchan_tc_model(self._h, out), "gpuchan_tc_model")
+        return tuple(int(v) for v in out)
+
     def discard(self):
         _check(self._L.gpuchan_discard(self._h), "gpuchan_discard")
 
     @property
     def in_flight(self):
         return self._L.gpuchan_in_flight(self._h)
+
+
+FANOUT_HOST, FANOUT_RELAY = 0, 1
+
+
+class GpuChanMulti:
+    """One process, several GPUs (gpuchan_multi_*): all channels of a configuration sharded over `devices`."""
+
+    def __init__(self, lpf_taps, offsets_hz, sample_rate_hz, decimation, max_batch_samples, devices, gains=None,
+                 flags=F_ATAN_FMA, engine=ENGINE_AUTO, fanout=FANOUT_HOST):
+        L = self._L = _lib.lib()
+        self._lpf = np.ascontiguousarray(lpf_taps, dtype=np.float64)
+        self._offs = np.ascontiguousarray(offsets_hz, dtype=np.int32)
+        self._gains = None if gains is None else np.ascontiguousarray(gains, dtype=np.float64)
+        self._devs = np.ascontiguousarray(devices, dtype=np.int32)
+        cfg = _lib.GpuChanCfg()
+        cfg.struct_size = C.sizeof(_lib.GpuChanCfg)
+        cfg.sample_rate_hz = int(sample_rate_hz)
+        cfg.decimation = int(decimation)
+        cfg.nr_taps = len(self._lpf)
+        cfg.nr_channels = len(self._offs)
+        cfg.max_batch_samples = int(max_batch_samples)
+        cfg.flags = int(flags)
+        cfg.engine = int(engine)
+        cfg.lpf_taps = self._lpf.ctypes.data_as(C.POINTER(C.c_double))
+        cfg.offset_hz = self._offs.ctypes.data_as(C.POINTER(C.c_int32))
+        cfg.gain = self._gains.ctypes.data_as(C.POINTER(C.c_double)) if self._gains is not None else None
+        self._h = C.c_void_p()
+        _check(L.gpuchan_multi_create(C.byref(self._h), C.byref(cfg), self._devs.ctypes.data, len(self._devs), int(fanout)),
+               "gpuchan_multi_create")
+        self.nr_channels = len(self._offs)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.gpuchan_multi_destroy(C.byref(self._h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit(self, iq_host: np.ndarray):
+        assert iq_host.dtype == np.int16 and iq_host.flags.c_contiguous
+        self._keep = iq_host
+        _check(self._L.gpuchan_multi_submit(self._h, iq_host.ctypes.data, len(iq_host) // 2), "gpuchan_multi_submit")
+
+    def pending(self) -> int:
+        n = C.c_size_t(0)
+        _check(self._L.gpuchan_multi_pending(self._h, C.byref(n)), "gpuchan_multi_pending")
+        return n.value
+
+    def collect(self) -> np.ndarray:
+        k = self.pending()
+        out = np.zeros((self.nr_channels, max(k, 1)), np.int16)
+        n = C.c_size_t(0)
+        _check(self._L.gpuchan_multi_collect(self._h, out.ctypes.data, out.shape[1], C.byref(n)), "gpuchan_multi_collect")
+        return out[:, :n.value]
+
+    def sync(self):
+        _check(self._L.gpuchan_multi_sync(self._h), "gpuchan_multi_sync")
+
+    @property
+    def devices(self):
+        return self._L.gpuchan_multi_devices(self._h)
+
+    def bank_range(self, i):
+        first, cnt = C.c_uint32(0), C.c_uint32(0)
+        _check(self._L.gpuchan_multi_bank(self._h, i, None, C.byref(first), C.byref(cnt)), "gpuchan_multi_bank")
+        return first.value, cnt.value

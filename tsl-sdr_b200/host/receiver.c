@@ -98,17 +98,38 @@ static void put_alnum_char(FILE *fp, char ch)
     }
 }
 
-static int on_pocsag_msg(struct receiver *rx, const char *type, uint32_t channel, uint16_t baud, uint32_t capcode,
-                         const char *data, size_t len, uint8_t function)
+/* Where a channel's lines go.  With one output for all channels every line carries "channel":N (our extension: the
+ * reference runs one decoder process per channel, so its lines need no such key).  With pagerDecode.outFile containing
+ * %u there is one file per channel and the lines are byte for byte what decoder.c prints. */
+static FILE *line_out(struct receiver *rx, uint32_t channel, bool *with_key)
+{
+    if (rx->msg_out_ch && channel < rx->nr_demod_threads && rx->msg_out_ch[channel]) { *with_key = false; return rx->msg_out_ch[channel]; }
+    *with_key = true;
+    return rx->msg_out;
+}
+
+static void put_timestamp(FILE *fp)
 {
     time_t now = time(NULL);
     struct tm gmt;
     gmtime_r(&now, &gmt);
-    FILE *fp = rx->msg_out;
-    fprintf(fp, "{\"proto\":\"pocsag\",\"type\":\"%s\",\"timestamp\":\"%04i-%02i-%02i %02i:%02i:%02i UTC\","
-            "\"baud\":%i,\"capCode\":%u,\"function\":%u,\"channel\":%u,\"message\":\"", type,
-            gmt.tm_year + 1900, gmt.tm_mon + 1, gmt.tm_mday, gmt.tm_hour, gmt.tm_min, gmt.tm_sec,
-            baud, capcode, (unsigned)function, channel);
+    fprintf(fp, "\"timestamp\":\"%04i-%02i-%02i %02i:%02i:%02i UTC\",", gmt.tm_year + 1900, gmt.tm_mon + 1, gmt.tm_mday,
+            gmt.tm_hour, gmt.tm_min, gmt.tm_sec);
+}
+
+/* decoder/decoder.c:264-318 */
+static int on_pocsag_msg(struct receiver_pager *pg, const char *type, uint32_t row, uint16_t baud, uint32_t capcode,
+                         const char *data, size_t len, uint8_t function)
+{
+    struct receiver *rx = pg->rx;
+    const uint32_t channel = pg->channel_base + row;
+    bool key;
+    FILE *fp = line_out(rx, channel, &key);
+    fprintf(fp, "{\"proto\":\"pocsag\",\"type\":\"%s\",", type);
+    put_timestamp(fp);
+    fprintf(fp, "\"baud\":%i,\"capCode\":%u,\"function\":%u,", baud, capcode, (unsigned)function);
+    if (key) fprintf(fp, "\"channel\":%u,", channel);
+    fputs("\"message\":\"", fp);
     for (size_t i = 0; i < len; i++) put_alnum_char(fp, data[i]);
     fputs("\"}\n", fp);
     fflush(fp);
@@ -126,57 +147,59 @@ static int on_numeric(void *user, uint32_t ch, uint16_t baud, uint32_t cap, cons
     return on_pocsag_msg(user, "numeric", ch, baud, cap, d, n, fn);
 }
 
-/* ---- FLEX JSON lines: decoder/decoder.c:173-262 (same keys, same order, plus "channel") ---- */
+/* ---- FLEX JSON lines: decoder/decoder.c:173-262 (same keys, same order) ---- */
 static const char flex_phase_id[4] = { 'A', 'B', 'C', 'D' };
 
-static void flex_head(struct receiver *rx, const char *type, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no,
-                      uint8_t frame_no, uint64_t cap_code)
+static FILE *flex_head(struct receiver_pager *pg, const char *type, uint32_t row, uint16_t baud, uint8_t phase, uint8_t cycle_no,
+                       uint8_t frame_no, uint64_t cap_code)
 {
-    time_t now = time(NULL);
-    struct tm gmt;
-    gmtime_r(&now, &gmt);
-    fprintf(rx->msg_out, "{\"proto\":\"flex\",\"type\":\"%s\",\"timestamp\":\"%04i-%02i-%02i %02i:%02i:%02i UTC\","
-            "\"baud\":%i,\"syncLevel\":%i,\"frameNo\":%u,\"cycleNo\":%u,\"phaseNo\":\"%c\",\"capCode\":%llu,\"channel\":%u,",
-            type, gmt.tm_year + 1900, gmt.tm_mon + 1, gmt.tm_mday, gmt.tm_hour, gmt.tm_min, gmt.tm_sec,
-            baud, 0, frame_no, cycle_no, flex_phase_id[phase & 3], (unsigned long long)cap_code, channel);
+    const uint32_t channel = pg->channel_base + row;
+    bool key;
+    FILE *fp = line_out(pg->rx, channel, &key);
+    fprintf(fp, "{\"proto\":\"flex\",\"type\":\"%s\",", type);
+    put_timestamp(fp);
+    fprintf(fp, "\"baud\":%i,\"syncLevel\":%i,\"frameNo\":%u,\"cycleNo\":%u,\"phaseNo\":\"%c\",\"capCode\":%llu,",
+            baud, 0, frame_no, cycle_no, flex_phase_id[phase & 3], (unsigned long long)cap_code);
+    if (key) fprintf(fp, "\"channel\":%u,", channel);
+    return fp;
 }
 
-static int on_flex_alnum(void *user, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no, uint8_t frame_no,
+static int on_flex_alnum(void *user, uint32_t row, uint16_t baud, uint8_t phase, uint8_t cycle_no, uint8_t frame_no,
                          uint64_t cap_code, int fragmented, int maildrop, uint8_t seq_num, const char *msg, size_t len)
 {
-    struct receiver *rx = user;
-    flex_head(rx, "alphanumeric", channel, baud, phase, cycle_no, frame_no, cap_code);
-    fprintf(rx->msg_out, "\"fragment\":%s,\"maildrop\":%s,\"fragSeq\":%u,\"message\":\"", fragmented ? "true" : "false",
+    struct receiver_pager *pg = user;
+    FILE *fp = flex_head(pg, "alphanumeric", row, baud, phase, cycle_no, frame_no, cap_code);
+    fprintf(fp, "\"fragment\":%s,\"maildrop\":%s,\"fragSeq\":%u,\"message\":\"", fragmented ? "true" : "false",
             maildrop ? "true" : "false", seq_num);
-    for (size_t i = 0; i < len; i++) put_alnum_char(rx->msg_out, msg[i]);
-    fputs("\"}\n", rx->msg_out);
-    fflush(rx->msg_out);
-    rx->nr_messages++;
+    for (size_t i = 0; i < len; i++) put_alnum_char(fp, msg[i]);
+    fputs("\"}\n", fp);
+    fflush(fp);
+    pg->rx->nr_messages++;
     return 0;
 }
 
-static int on_flex_num(void *user, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no, uint8_t frame_no,
+static int on_flex_num(void *user, uint32_t row, uint16_t baud, uint8_t phase, uint8_t cycle_no, uint8_t frame_no,
                        uint64_t cap_code, const char *msg, size_t len)
 {
-    struct receiver *rx = user;
-    flex_head(rx, "numeric", channel, baud, phase, cycle_no, frame_no, cap_code);
-    fputs("\"message\":\"", rx->msg_out);
-    for (size_t i = 0; i < len; i++) put_alnum_char(rx->msg_out, msg[i]);
-    fputs("\"}\n", rx->msg_out);
-    fflush(rx->msg_out);
-    rx->nr_messages++;
+    struct receiver_pager *pg = user;
+    FILE *fp = flex_head(pg, "numeric", row, baud, phase, cycle_no, frame_no, cap_code);
+    fputs("\"message\":\"", fp);
+    for (size_t i = 0; i < len; i++) put_alnum_char(fp, msg[i]);
+    fputs("\"}\n", fp);
+    fflush(fp);
+    pg->rx->nr_messages++;
     return 0;
 }
 
-static int on_flex_siv(void *user, uint32_t channel, uint16_t baud, uint8_t phase, uint8_t cycle_no, uint8_t frame_no,
+static int on_flex_siv(void *user, uint32_t row, uint16_t baud, uint8_t phase, uint8_t cycle_no, uint8_t frame_no,
                        uint64_t cap_code, uint8_t siv_msg_type, uint32_t data)
 {
-    struct receiver *rx = user;
+    struct receiver_pager *pg = user;
     if (siv_msg_type != 0) return 0;            /* decoder.c:249-257 prints temporary address activations only */
-    flex_head(rx, "tempAddrActivation", channel, baud, phase, cycle_no, frame_no, cap_code);
-    fprintf(rx->msg_out, "\"startFrameNo\":%u,\"tempAddressId\":%u}\n", data & 0x7f, (data >> 7) & 0xf);
-    fflush(rx->msg_out);
-    rx->nr_messages++;
+    FILE *fp = flex_head(pg, "tempAddrActivation", row, baud, phase, cycle_no, frame_no, cap_code);
+    fprintf(fp, "\"startFrameNo\":%u,\"tempAddressId\":%u}\n", data & 0x7f, (data >> 7) & 0xf);
+    fflush(fp);
+    pg->rx->nr_messages++;
     return 0;
 }
 
@@ -211,13 +234,18 @@ static void write_outputs(struct receiver *rx, size_t n_out)
 static void collect_one(struct receiver *rx)
 {
     size_t n_out = 0;
-    if (gpuchan_collect(rx->bank, rx->pcm_host, rx->pcm_cap, &n_out)) {
+    if (gpuchan_multi_collect(rx->bank, rx->pcm_host, rx->pcm_cap, &n_out)) {
         B200_MSG("F", "GPU-COLLECT", "%s", gpuchan_last_error());
         abort();
     }
-    if (rx->iq_host) {
-        size_t n_iq = 0;
-        gpuchan_collect_iq(rx->bank, rx->iq_host, rx->pcm_cap, &n_iq);
+    if (rx->iq_host) {                          /* signalDebugFile taps: per bank, each its own channel range */
+        for (uint32_t d = 0; d < gpuchan_multi_devices(rx->bank); d++) {
+            gpuchan_t *bank = NULL;
+            uint32_t first = 0, cnt = 0;
+            size_t n_iq = 0;
+            gpuchan_multi_bank(rx->bank, d, &bank, &first, &cnt);
+            gpuchan_collect_iq(bank, rx->iq_host + 2 * (size_t)first * rx->pcm_cap, rx->pcm_cap, &n_iq);
+        }
     }
     if (n_out) write_outputs(rx, n_out);
     rx->in_flight--;
@@ -226,23 +254,31 @@ static void collect_one(struct receiver *rx)
 static void submit_batch(struct receiver *rx)
 {
     if (0 == rx->batch_fill) return;
-    if (gpuchan_submit(rx->bank, rx->batch[rx->batch_cur], rx->batch_fill)) {
+    if (gpuchan_multi_submit(rx->bank, rx->batch[rx->batch_cur], rx->batch_fill)) {
         B200_MSG("F", "GPU-SUBMIT", "%s", gpuchan_last_error());
         abort();
     }
     rx->total_iq_samples += rx->batch_fill;
-    if (rx->pager) {
+    /* in-process decoders: every pager bank reads its rows of its device's PCM (still on that device); all banks are fed
+     * first, the callbacks fire afterwards, so the devices decode side by side */
+    for (size_t p = 0; p < rx->nr_pagers; p++) {
+        struct receiver_pager *pg = &rx->pagers[p];
+        gpuchan_t *bank = NULL;
         const int16_t *d_pcm = NULL;
         size_t pitch = 0, n = 0;
-        gpuchan_device_pcm(rx->bank, &d_pcm, &pitch, &n);
-        gpuchan_sync(rx->bank);                 /* pager stream is ordered after the bank's work */
-        if (n && gpupager_feed_device(rx->pager, d_pcm, pitch, n, NULL)) {
+        gpuchan_multi_bank(rx->bank, pg->device_index, &bank, NULL, NULL);
+        gpuchan_device_pcm(bank, &d_pcm, &pitch, &n);
+        gpuchan_sync(bank);                     /* pager stream is ordered after the bank's work */
+        if (n && gpupager_feed_device(pg->bank, d_pcm, pitch, n, NULL)) {
             B200_MSG("F", "GPU-PAGER", "%s", gpupager_last_error());
             abort();
         }
+    }
+    for (size_t p = 0; p < rx->nr_pagers; p++) {
+        struct receiver_pager *pg = &rx->pagers[p];
         size_t nr = 0;
-        if (rx->pager_is_flex) gpupager_dispatch_flex(rx->pager, on_flex_alnum, on_flex_num, on_flex_siv, rx, &nr);
-        else gpupager_dispatch(rx->pager, on_numeric, on_alpha, rx, &nr);
+        if (pg->is_flex) gpupager_dispatch_flex(pg->bank, on_flex_alnum, on_flex_num, on_flex_siv, pg, &nr);
+        else gpupager_dispatch(pg->bank, on_numeric, on_alpha, pg, &nr);
     }
     rx->in_flight++;
     rx->batch_cur ^= 1;
@@ -341,8 +377,23 @@ aresult_t receiver_init(struct receiver *rx, const jnode *cfg, receiver_rx_threa
     }
 
     /* our extensions (all optional) */
-    rx->gpu_device = 0; rx->batch_bufs = 64;
-    if (!json_get_int(cfg, "gpuDevice", &v)) rx->gpu_device = v;
+    rx->batch_bufs = 64;
+    rx->gpu_devices[0] = 0; rx->nr_gpu_devices = 1; rx->gpu_fanout = GPUCHAN_FANOUT_HOST;
+    if (!json_get_int(cfg, "gpuDevice", &v)) rx->gpu_devices[0] = v;
+    const jnode *gd = json_get(cfg, "gpuDevices");          /* channels shard over these devices (contiguous ranges) */
+    if (gd && gd->type == J_ARR && gd->len > 0) {
+        if (gd->len > 16) { B200_MSG("E", "BAD-GPU-DEVICES", "at most 16 gpuDevices"); return A_E_INVAL; }
+        rx->nr_gpu_devices = (uint32_t)gd->len;
+        for (size_t i = 0; i < gd->len; i++) {
+            if (gd->items[i]->type != J_NUM || !gd->items[i]->is_int) { B200_MSG("E", "BAD-GPU-DEVICES", "gpuDevices[%zu] is not an integer", i); return A_E_INVAL; }
+            rx->gpu_devices[i] = (int)gd->items[i]->inum;
+        }
+    }
+    const char *fo = NULL;
+    if (!json_get_string(cfg, "gpuFanout", &fo)) {
+        if (!strcmp(fo, "relay")) rx->gpu_fanout = GPUCHAN_FANOUT_RELAY;
+        else if (strcmp(fo, "host")) { B200_MSG("E", "BAD-GPU-FANOUT", "gpuFanout must be \"host\" or \"relay\""); return A_E_INVAL; }
+    }
     if (!json_get_int(cfg, "gpuBatchBuffers", &v) && v > 0) rx->batch_bufs = (size_t)v;
 
     /* pool */
@@ -369,56 +420,102 @@ aresult_t receiver_init(struct receiver *rx, const jnode *cfg, receiver_rx_threa
     memset(&gc, 0, sizeof(gc));
     gc.struct_size = sizeof(gc);
     gc.sample_rate_hz = rx->sample_rate_hz; gc.decimation = rx->decimation;
-    gc.nr_taps = (uint32_t)rx->nr_lpf_taps; gc.nr_channels = (uint32_t)C; gc.device = rx->gpu_device;
+    gc.nr_taps = (uint32_t)rx->nr_lpf_taps; gc.nr_channels = (uint32_t)C;
     gc.max_batch_samples = (uint32_t)(rx->batch_bufs * samples_per_buf);
     gc.flags = GPUCHAN_F_DEFAULT | (any_debug ? GPUCHAN_F_KEEP_IQ : 0);
     gc.lpf_taps = rx->lpf_taps; gc.offset_hz = offs; gc.gain = gains;
-    gpuchan_t *bank = NULL;
-    int rc = gpuchan_create(&bank, &gc);
+    gpuchan_multi_t *bank = NULL;
+    int rc = gpuchan_multi_create(&bank, &gc, rx->gpu_devices, rx->nr_gpu_devices, rx->gpu_fanout);
     free(offs); free(gains);
-    if (rc) { B200_MSG("E", "GPU-BANK", "gpuchan_create failed: %s", gpuchan_last_error()); return A_E_INVAL; }
+    if (rc) { B200_MSG("E", "GPU-BANK", "gpuchan_multi_create failed: %s", gpuchan_last_error()); return A_E_INVAL; }
     rx->bank = bank;
+    if (gpuchan_multi_devices(bank) > 1)
+        B200_MSG("I", "GPU-DEVICES", "%zu channels sharded over %u GPUs, IQ fan-out: %s", C, gpuchan_multi_devices(bank),
+                 rx->gpu_fanout == GPUCHAN_FANOUT_RELAY ? "NVLink relay chain" : "one PCIe copy per GPU");
     rx->pcm_cap = gc.max_batch_samples / rx->decimation + 64;
     for (int i = 0; i < 2; i++)
         if (gpuchan_host_alloc((void **)&rx->batch[i], (size_t)gc.max_batch_samples * 4)) return A_E_NOMEM;
     if (gpuchan_host_alloc((void **)&rx->pcm_host, C * rx->pcm_cap * sizeof(int16_t))) return A_E_NOMEM;
     if (any_debug && gpuchan_host_alloc((void **)&rx->iq_host, C * rx->pcm_cap * 4)) return A_E_NOMEM;
 
-    /* optional in-process decoder (one `decoder -m POCSAG -I i -D d -F taps` per channel in the reference) */
+    /* optional in-process decoders.  The reference runs one `decoder -m <proto> -I i -D d -F taps [-b] [-i]` process per
+     * channel FIFO (decoder/decoder.c:685-697); here pagerDecode is one such specification for all channels, or an array
+     * of them, each naming its channels ("channels": [indices into the channels array]) -- a mixed POCSAG / FLEX
+     * receiver.  Every specification becomes one pager bank per device that owns some of its channels. */
     const jnode *pd = json_get(cfg, "pagerDecode");
     rx->msg_out = stdout;
-    if (pd && pd->type == J_OBJ) {
+    const size_t nr_specs = !pd ? 0 : (pd->type == J_ARR ? pd->len : (pd->type == J_OBJ ? 1 : 0));
+    if (nr_specs) rx->pagers = calloc(nr_specs * gpuchan_multi_devices(bank), sizeof(*rx->pagers));
+    for (size_t sp = 0; sp < nr_specs; sp++) {
+        const jnode *spec = pd->type == J_ARR ? pd->items[sp] : pd;
+        if (!spec || spec->type != J_OBJ) { B200_MSG("E", "PAGER-SPEC", "pagerDecode[%zu] is not an object", sp); return A_E_INVAL; }
         int I = 1, Dd = 1;
         const char *s = NULL;
-        json_get_int(pd, "interpolate", &I); json_get_int(pd, "decimate", &Dd);
-        const jnode *co = json_get(pd, "lpfCoeffs");
+        json_get_int(spec, "interpolate", &I); json_get_int(spec, "decimate", &Dd);
+        const jnode *co = json_get(spec, "lpfCoeffs");
         if (!co || co->type != J_ARR || co->len == 0) { B200_MSG("E", "PAGER-TAPS", "pagerDecode.lpfCoeffs missing"); return A_E_INVAL; }
         double *cf = calloc(co->len, sizeof(double));
         int16_t *q = calloc(co->len, sizeof(int16_t));
         for (size_t i = 0; i < co->len; i++) cf[i] = co->items[i]->num;
         gpupager_quantize_taps(cf, co->len, q);
-        gpupager_cfg pc;
-        memset(&pc, 0, sizeof(pc));
-        pc.struct_size = sizeof(pc); pc.nr_channels = (uint32_t)C; pc.device = rx->gpu_device;
-        pc.interpolate = (uint32_t)I; pc.decimate = (uint32_t)Dd; pc.nr_taps = (uint32_t)co->len;
-        pc.max_feed_samples = (uint32_t)rx->pcm_cap; pc.taps = q;
-        double pole = 0.0;
-        if (!json_get_double(pd, "dcBlockPole", &pole)) { pc.flags |= GPUPAGER_F_DC_BLOCK; pc.dc_pole = pole; }
-        const char *proto = NULL;                           /* decoder -m POCSAG | FLEX */
-        if (!json_get_string(pd, "protocol", &proto) && !strncasecmp(proto, "flex", 4)) {
-            pc.decoder = GPUPAGER_DECODER_FLEX;
-            rx->pager_is_flex = true;
+        free(cf);
+        /* which channels this specification decodes */
+        bool *sel = calloc(C, sizeof(bool));
+        const jnode *chs = json_get(spec, "channels");
+        if (chs && chs->type == J_ARR) {
+            for (size_t i = 0; i < chs->len; i++) {
+                const jnode *e = chs->items[i];
+                if (e->type != J_NUM || !e->is_int || e->inum < 0 || (size_t)e->inum >= C) {
+                    B200_MSG("E", "PAGER-CHANNELS", "pagerDecode channels[%zu] is not a channel index", i);
+                    free(sel); free(q);
+                    return A_E_INVAL;
+                }
+                sel[e->inum] = true;
+            }
+        } else {
+            for (size_t i = 0; i < C; i++) sel[i] = true;
         }
-        int inv = 0;                                        /* decoder -i */
-        if (!json_get_int(pd, "invert", &inv) && inv) pc.flags |= GPUPAGER_F_INVERT;
-        gpupager_t *pg = NULL;
-        rc = gpupager_create(&pg, &pc);
-        free(cf); free(q);
-        if (rc) { B200_MSG("E", "GPU-PAGER", "gpupager_create failed: %s", gpupager_last_error()); return A_E_INVAL; }
-        rx->pager = pg;
-        if (!json_get_string(pd, "outFile", &s)) {
-            rx->msg_out = fopen(s, "w");
-            if (!rx->msg_out) { B200_MSG("E", "PAGER-OUT", "cannot open %s", s); return A_E_INVAL; }
+        const char *proto = NULL;                           /* decoder -m POCSAG | FLEX */
+        const bool is_flex = !json_get_string(spec, "protocol", &proto) && !strncasecmp(proto, "flex", 4);
+        for (uint32_t d = 0; d < gpuchan_multi_devices(bank); d++) {
+            uint32_t first = 0, cnt = 0, nsel = 0;
+            gpuchan_multi_bank(bank, d, NULL, &first, &cnt);
+            uint32_t *map = calloc(cnt ? cnt : 1, sizeof(uint32_t));
+            for (uint32_t r = 0; r < cnt; r++) if (sel[first + r]) map[nsel++] = r;
+            if (nsel) {
+                gpupager_cfg pc;
+                memset(&pc, 0, sizeof(pc));
+                pc.struct_size = sizeof(pc); pc.nr_channels = nsel; pc.device = rx->gpu_devices[d];
+                pc.interpolate = (uint32_t)I; pc.decimate = (uint32_t)Dd; pc.nr_taps = (uint32_t)co->len;
+                pc.max_feed_samples = (uint32_t)rx->pcm_cap; pc.taps = q;
+                pc.channel_map = map;
+                double pole = 0.0;
+                if (!json_get_double(spec, "dcBlockPole", &pole)) { pc.flags |= GPUPAGER_F_DC_BLOCK; pc.dc_pole = pole; }
+                if (is_flex) pc.decoder = GPUPAGER_DECODER_FLEX;
+                int inv = 0;                                /* decoder -i */
+                if (!json_get_int(spec, "invert", &inv) && inv) pc.flags |= GPUPAGER_F_INVERT;
+                struct receiver_pager *pg = &rx->pagers[rx->nr_pagers];
+                rc = gpupager_create(&pg->bank, &pc);
+                if (rc) { B200_MSG("E", "GPU-PAGER", "gpupager_create failed: %s", gpupager_last_error()); free(map); free(sel); free(q); return A_E_INVAL; }
+                pg->rx = rx; pg->is_flex = is_flex; pg->device_index = d; pg->channel_base = first;
+                rx->nr_pagers++;
+            }
+            free(map);
+        }
+        free(sel); free(q);
+        if (!json_get_string(spec, "outFile", &s) && rx->msg_out == stdout && !rx->msg_out_ch) {
+            if (strstr(s, "%u")) {                          /* one file per channel, decoder.c's lines byte for byte */
+                rx->msg_out_ch = calloc(C, sizeof(FILE *));
+                for (size_t i = 0; i < C; i++) {
+                    char path[4096];
+                    snprintf(path, sizeof(path), s, (unsigned)i);
+                    rx->msg_out_ch[i] = fopen(path, "w");
+                    if (!rx->msg_out_ch[i]) { B200_MSG("E", "PAGER-OUT", "cannot open %s", path); return A_E_INVAL; }
+                }
+            } else {
+                rx->msg_out = fopen(s, "w");
+                if (!rx->msg_out) { B200_MSG("E", "PAGER-OUT", "cannot open %s", s); return A_E_INVAL; }
+            }
         }
     }
 
@@ -434,7 +531,7 @@ aresult_t receiver_init(struct receiver *rx, const jnode *cfg, receiver_rx_threa
             if (ch->debug_fd < 0) { B200_MSG("F", "CANT-OPEN-SIGNAL-DEBUG", "Unable to open signal debug dump file '%s'", ch->signal_debug); return A_E_INVAL; }
             if (0 == fstat(ch->debug_fd, &sb) && S_ISREG(sb.st_mode) && ftruncate(ch->debug_fd, 0)) { /* keep going */ }
         }
-        if (strcmp(ch->out_fifo, "/dev/null") == 0 && rx->pager) continue;     /* decode-only channel */
+        if (strcmp(ch->out_fifo, "/dev/null") == 0 && rx->nr_pagers) continue;  /* decode-only channel */
         ch->fifo_fd = open(ch->out_fifo, O_WRONLY);
         if (ch->fifo_fd < 0) { B200_MSG("F", "CANT-OPEN-FIFO", "Unable to open output fifo '%s'", ch->out_fifo); return A_E_INVAL; }
         if (0 == fstat(ch->fifo_fd, &sb) && S_ISREG(sb.st_mode) && ftruncate(ch->fifo_fd, 0)) { /* keep going */ }
@@ -484,11 +581,16 @@ aresult_t receiver_cleanup(struct receiver **prx)
         if (ch->debug_fd >= 0) close(ch->debug_fd);
         free(ch->out_fifo); free(ch->signal_debug);
     }
-    if (rx->pager) gpupager_destroy((gpupager_t **)&rx->pager);
-    if (rx->bank) gpuchan_destroy((gpuchan_t **)&rx->bank);
+    for (size_t p = 0; p < rx->nr_pagers; p++) gpupager_destroy(&rx->pagers[p].bank);
+    free(rx->pagers);
+    if (rx->bank) gpuchan_multi_destroy(&rx->bank);
     gpuchan_host_free(rx->batch[0]); gpuchan_host_free(rx->batch[1]);
     gpuchan_host_free(rx->pcm_host); gpuchan_host_free(rx->iq_host);
     if (rx->msg_out && rx->msg_out != stdout) fclose(rx->msg_out);
+    if (rx->msg_out_ch) {
+        for (size_t i = 0; i < rx->nr_demod_threads; i++) if (rx->msg_out_ch[i]) fclose(rx->msg_out_ch[i]);
+        free(rx->msg_out_ch);
+    }
     for (int i = 0; i < rx->nr_samp_bufs; i++) free(rx->pool[i]);   /* all buffers are back in the pool by now */
     free(rx->pool); free(rx->channels); free(rx->lpf_taps);
     pthread_mutex_destroy(&rx->pool_mtx); pthread_mutex_destroy(&rx->q_mtx); pthread_cond_destroy(&rx->q_cv);

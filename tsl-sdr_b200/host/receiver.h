@@ -14,8 +14,18 @@ struct receiver;
 typedef aresult_t (*receiver_cleanup_func_t)(struct receiver *rx);
 typedef aresult_t (*receiver_rx_thread_func_t)(struct receiver *rx);
 
-struct gpuchan;
+struct gpuchan_multi;
 struct gpupager;
+
+/* one in-process decoder bank: a protocol + resampler for a set of channels living on one device (the reference runs one
+ * `decoder` process per channel and picks protocol and resampler per process, decoder/decoder.c:685-697) */
+struct receiver_pager {
+    struct gpupager *bank;
+    struct receiver *rx;
+    bool is_flex;
+    uint32_t device_index;              /* which bank of the multi-device channel bank feeds it */
+    uint32_t channel_base;              /* first channel of that bank: reported channel = base + row */
+};
 
 struct receiver_channel {
     char *out_fifo;             /* channels[].outFifo */
@@ -53,10 +63,12 @@ struct receiver {
     pthread_cond_t q_cv;
 
     /* GPU consumer */
-    struct gpuchan *bank;
-    struct gpupager *pager;
-    bool pager_is_flex;                 /* pagerDecode.protocol == "flex" (decoder -m FLEX) */
-    int gpu_device;
+    struct gpuchan_multi *bank;         /* all channels, sharded over gpuDevices (one device by default) */
+    struct receiver_pager *pagers;      /* pagerDecode: one entry per (decoder spec, device) */
+    size_t nr_pagers;
+    int gpu_devices[16];
+    uint32_t nr_gpu_devices;
+    uint32_t gpu_fanout;                /* gpuFanout: "host" (default) | "relay" */
     size_t batch_bufs;                  /* sample_bufs per GPU submit (gpuBatchBuffers, default 64) */
     int16_t *batch[2];                  /* pinned staging, double buffered */
     size_t batch_fill;
@@ -66,6 +78,7 @@ struct receiver {
     int16_t *iq_host;
     size_t pcm_cap;
     FILE *msg_out;                      /* pagerDecode.outFile or stdout */
+    FILE **msg_out_ch;                  /* outFile with a %u: one file per channel, lines exactly as decoder.c prints them */
     size_t nr_messages;
     uint64_t total_iq_samples;
 
