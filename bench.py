@@ -124,6 +124,15 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi needs about a second to start: do not begin the timed region before it is sampling"""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            self.f.flush()
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.05)
+
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -378,15 +387,22 @@ def main():
     barrier()
 
     # ---------------- device-resident throughput ("value") ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup * S):
         submit_resident()
+    if rank == 0:
+        sampler.wait_first_sample()
+        for _ in range(S):                              # the GPU idled while nvidia-smi started: one more warm-up step
+            submit_resident()
+    else:
+        for _ in range(S):
+            submit_resident()
     barrier()
     bank.timing_read()
     bank.timing_enable(True)
     launches0 = bank.kernel_launches
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()

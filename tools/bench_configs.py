@@ -19,7 +19,16 @@ tslb200_loader.load_package()
 from tsl_sdr_b200 import synth  # noqa: E402
 from tsl_sdr_b200.gpuchan import GpuChan, F_ATAN_FMA  # noqa: E402
 
-SHAPES = [   # name, C, fs, T, D, cutoff
+def shipped_taps(name):
+    """a low-pass prototype as the reference ships it (etc/*.json: 256-tap etc/pocsag_1200khz_fs.json, 512-tap
+    etc/flex_25khz_lpf_3mhz.json); regenerated with the same design parameters because /root/reference does not travel"""
+    if name == "pocsag_1200khz_fs":
+        return synth.lowpass_taps(256, 9000.0, 1_200_000)
+    return synth.lowpass_taps(512, 9000.0, 3_000_000)
+
+
+# (name, C, fs, T, D, cutoff[, dBGain[, shipped tap set]])
+SHAPES = [
     ("c1  1 ch x 127 taps, D=100, 2.4 MS/s", 1, 2_400_000, 127, 100, 9000.0),
     ("c2  64 ch x 127 taps, D=100, 2.4 MS/s", 64, 2_400_000, 127, 100, 9000.0),
     ("c3  256 ch x 127 taps, D=25, 1.2 MS/s", 256, 1_200_000, 127, 25, 9000.0),
@@ -28,6 +37,13 @@ SHAPES = [   # name, C, fs, T, D, cutoff
     ("c4' 1024 ch x 255 taps, D=200, 10 MS/s on one GPU", 1024, 10_000_000, 255, 200, 12000.0),
     ("c5  256 ch x 512 taps, D=120, 3 MS/s", 256, 3_000_000, 512, 120, 9000.0),
     ("headline 256 ch x 127 taps, D=100, 2.4 MS/s", 256, 2_400_000, 127, 100, 9000.0),
+    # gain coverage: dBGain is applied as 10^(dB/10) to the taps (multifm/receiver.c:220); beyond |tap| = 508 the int8 sum split
+    # no longer fits and the engine switches to radix-256 limbs (4 MMAs per K chunk instead of 2, 3 accumulators)
+    ("headline + dBGain 4 (sum split, 3 terms)", 256, 2_400_000, 127, 100, 9000.0, 4.0),
+    ("headline + dBGain 8 (radix split)", 256, 2_400_000, 127, 100, 9000.0, 8.0),
+    ("c2 + dBGain 8 (radix split)", 64, 2_400_000, 127, 100, 9000.0, 8.0),
+    ("c3 with the shipped 256-tap etc/pocsag_1200khz_fs.json design, dBGain 4 (etc/pocsag_rtlsdr.json)", 256, 1_200_000, 256, 25, 9000.0, 4.0, "pocsag_1200khz_fs"),
+    ("c5 with the shipped 512-tap etc/flex_25khz_lpf_3mhz.json design", 256, 3_000_000, 512, 120, 9000.0, 0.0, "flex_25khz_lpf_3mhz"),
 ]
 
 
@@ -40,11 +56,13 @@ def main():
     n = 1 << int(os.environ.get("BATCH_LOG2", "24"))
     rng = np.random.default_rng(1)
     iq = np.clip(np.round(rng.normal(0, 3000, 2 * n)), -32768, 32767).astype(np.int16)
-    for name, C, fs, T, D, cut in SHAPES:
-        lpf = synth.lowpass_taps(T, cut, fs)
+    for name, C, fs, T, D, cut, *rest in SHAPES:
+        gain_db = rest[0] if rest else 0.0
+        lpf = shipped_taps(rest[1]) if len(rest) > 1 else synth.lowpass_taps(T, cut, fs)
         offs = synth.channel_offsets(C, fs)
+        gains = None if not gain_db else [10.0 ** (gain_db / 10.0)] * C
         try:
-            bank = GpuChan(lpf, offs, fs, D, n, flags=F_ATAN_FMA, engine=int(os.environ.get("ENGINE", "0")))
+            bank = GpuChan(lpf, offs, fs, D, n, gains=gains, flags=F_ATAN_FMA, engine=int(os.environ.get("ENGINE", "0")))
         except Exception as exc:
             print(json.dumps({"shape": name, "error": str(exc)}))
             continue
@@ -62,7 +80,8 @@ def main():
         ms, cnt = bank.timing_read()
         ms /= max(1, cnt)
         alg = 4.0 * n + 2.0 * C * k
-        print(json.dumps({"shape": name, "engine": {1: "imad", 2: "tc"}.get(bank.engine, "?"), "kernel_ms": round(ms, 4),
+        mma_per_tile = bank.tc_model()[0]
+        print(json.dumps({"shape": name, "engine": {1: "imad", 2: "tc"}.get(bank.engine, "?"), "mma_per_tile": mma_per_tile, "kernel_ms": round(ms, 4),
                           "channel_samples_per_s": C * k / (ms * 1e-3), "iq_msps": n / (ms * 1e-3) / 1e6,
                           "alg_GBps": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak,
                           "int16_mac_per_s": 4.0 * T * C * k / (ms * 1e-3)}))

@@ -673,8 +673,16 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
             const char *why = h->tc.why;
             free_all(h);
             return set_err(GPUCHAN_E_INVAL, "tensor-core engine unavailable: %s", why);
+        } else {
+            /* never silent: the exact CUDA-core engine is an order of magnitude slower */
+            fprintf(stderr, "gpuchan: tensor-core engine unavailable for %d taps, decimation %d, %d channels (%s): using the int32 CUDA-core "
+                            "engine (about 15x slower)\n", T, h->D, C, h->tc.why);
         }
     }
+    if (getenv("GPUCHAN_VERBOSE") && h->engine == GPUCHAN_ENGINE_TC)
+        fprintf(stderr, "gpuchan: tensor-core engine, tap limbs by %s (%d MMAs per 64-output tile, %d channel group%s, %d sample stages)\n",
+                h->tc.mode == TC_MODE_SUM ? "sum of int8 terms" : "radix 256", (int)h->tc.prog.size(), h->tc.G, h->tc.G == 1 ? "" : "s",
+                h->tc.nb_stages);
 
     /* --- pick the IMAD kernel variant that fits shared memory (also the fallback engine) --- */
     if (h->engine == GPUCHAN_ENGINE_IMAD) {
