@@ -180,9 +180,6 @@ int gpuchan_timing_read(gpuchan_t *h, double *total_ms, uint64_t *nr_launches);
  * tile, their N, PCM outputs per channel per tile, channel groups }; zeros on the IMAD engine. */
 int gpuchan_tc_model(gpuchan_t *h, uint64_t out[4]);
 
-/* Diagnostics (GPUCHAN_DEBUG_STAMPS=1 at create): clock64 stamps of CTA 0's roles, out = [3][32][8] int64. */
-int gpuchan_debug_stamps(gpuchan_t *h, long long *out);
-
 /* Unit hook for tests: one tcgen05 kind::i8 tile, D[128][N] = A0*B0[shift0..]^T + A1*B1[shift1..]^T (int32, wraps).
  * All pointers are host pointers; A is 128 x Kp bytes, B is R x Kp bytes, row-major. */
 int gpuchan_tc_selftest(const uint8_t *A0, const uint8_t *B0, const uint8_t *A1, const uint8_t *B1, int Kp, int R,

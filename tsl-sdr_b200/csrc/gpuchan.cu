@@ -492,10 +492,7 @@ struct gpuchan {
     /* tensor-core engine */
     TcPlan tc;
     uint8_t *d_tap_img = nullptr;
-    long long *d_dbg = nullptr;             /* role clock stamps (GPUCHAN_DEBUG_STAMPS=1) */
     int nr_sms = 148;
-    int tc_tune = 0;                        /* GPUCHAN_TC_TUNE: kernel experiment switches (tc_engine.cu) */
-    uint32_t tc_sleep[3] = { 0, 0, 0 };     /* GPUCHAN_TC_SLEEP="epi,xf,mma" ns: poll intervals (0 = default) */
 };
 
 static void host_atan_table(float2 *out)
@@ -581,7 +578,7 @@ static int free_all(gpuchan *h)
     cudaFree(h->d_last[0]); cudaFree(h->d_last[1]);
     cudaFree(h->d_mu); cudaFree(h->d_lambda); cudaFree(h->d_cyc);
     cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_ckpt);
-    cudaFree(h->d_atan); cudaFree(h->d_tap_img); cudaFree(h->d_dbg);
+    cudaFree(h->d_atan); cudaFree(h->d_tap_img);
     for (int i = 0; i < gpuchan::NSLOT; i++) {
         cudaFree(h->d_stage[i]); cudaFree(h->d_stage8[i]); cudaFree(h->d_pcm[i]); cudaFree(h->d_iq[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -707,12 +704,6 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
         tc_build_tap_image(h->tc, h->h_re.data(), h->h_im.data(), img);
         FAIL_TRY(cudaMalloc(&h->d_tap_img, img.size()));
         FAIL_TRY(cudaMemcpy(h->d_tap_img, img.data(), img.size(), cudaMemcpyHostToDevice));
-        if (getenv("GPUCHAN_TC_TUNE")) h->tc_tune = atoi(getenv("GPUCHAN_TC_TUNE"));
-        if (getenv("GPUCHAN_TC_SLEEP")) sscanf(getenv("GPUCHAN_TC_SLEEP"), "%u,%u,%u", &h->tc_sleep[0], &h->tc_sleep[1], &h->tc_sleep[2]);
-        if (getenv("GPUCHAN_DEBUG_STAMPS")) {
-            FAIL_TRY(cudaMalloc(&h->d_dbg, 3 * 32 * 8 * sizeof(long long)));
-            FAIL_TRY(cudaMemset(h->d_dbg, 0, 3 * 32 * 8 * sizeof(long long)));
-        }
     }
 
     FAIL_TRY(cudaMalloc(&h->d_taps, packed.size() * sizeof(int)));
@@ -758,13 +749,10 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
         FAIL_TRY(cudaMemcpy(mu.data(), h->d_mu, C * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         FAIL_TRY(cudaMemcpy(lam.data(), h->d_lambda, C * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         h->all_cyclic = true; h->mu_max = 0;
-        unsigned lam_max = 0;
         for (int c = 0; c < C; c++) {
             if (lam[c] == 0) h->all_cyclic = false;
             else if (mu[c] > h->mu_max) h->mu_max = mu[c];
-            if (lam[c] > lam_max) lam_max = lam[c];
         }
-        if (use_tc && (h->tc_tune & 8)) tc_plan_reserve_rot(h->tc, h->all_cyclic ? lam_max : 0, h->smem_max);
     }
 #undef FAIL_TRY
     *ph = h;
@@ -893,10 +881,6 @@ static int run_batch(gpuchan *h, const int *d_fresh, size_t n_complex, cudaStrea
             }
             if (keep > 0) { tb.carry_out = h->d_carry[h->pp_carry ^ 1]; tb.carry_from = from; tb.carry_keep = (int)keep; }
             tb.K = K; tb.geom = tg; tb.atan = h->atan;
-            tb.dbg = h->d_dbg;
-            tb.dbg_flags = (h->d_dbg && getenv("GPUCHAN_DEBUG_SKIP")) ? atoi(getenv("GPUCHAN_DEBUG_SKIP")) : 0;
-            tb.tune = h->tc_tune;
-            for (int i = 0; i < 3; i++) if (h->tc_sleep[i]) tb.sleep_ns[i] = h->tc_sleep[i];
             CUDA_TRY(tc_launch_fir_fm(h->tc, tb, st));
             h->launches++;
         } else {
@@ -1177,18 +1161,6 @@ extern "C" int gpuchan_host_alloc(void **pp, size_t bytes)
 extern "C" int gpuchan_host_free(void *p)
 {
     if (p) CUDA_TRY(cudaFreeHost(p));
-    return GPUCHAN_OK;
-}
-
-/* Diagnostics: clock stamps of CTA 0's producer / MMA / epilogue roles for the first 32 tiles of the last launch
- * (only when the bank was created with GPUCHAN_DEBUG_STAMPS set in the environment). out: [3][32][8] int64. */
-extern "C" int gpuchan_debug_stamps(gpuchan_t *h, long long *out)
-{
-    if (!h || !out) return set_err(GPUCHAN_E_BADARGS, "null argument");
-    if (!h->d_dbg) return set_err(GPUCHAN_E_INVAL, "stamps not enabled");
-    CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(out, h->d_dbg, 3 * 32 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     return GPUCHAN_OK;
 }
 

@@ -3,19 +3,21 @@
  * C ABI in include/tslb200_gpupager.h.
  *
  * Kernels:
- *   resample_kernel   one thread per (channel, output): y_m = rq(sum_j h_{p_m}[j] * x[n_m + j]),
- *                     n_m = floor(m*D/I), p_m = (m*D) mod I            (filter/polyphase_fir.c:184-227,
- *                                                                       filter/utils.c:46-116)
- *   pocsag_kernel     one thread per channel, sequential over the resampled 38400 Hz stream: optional DC
- *                     blocker (filter/dc_blocker.h:72-92), 3-rate eye sync detector, slicer, 16-word batch,
- *                     BCH(31,21) correction, address/alpha/numeric assembly (pager/pager_pocsag.c:82-543,
- *                     pager/bch_code.c:307-398).  Messages are queued per channel for the host callbacks.
+ *   resample_kernel   one thread per (channel, output), 256 outputs per block over a shared-memory input tile:
+ *                     y_m = rq(sum_j h_{p_m}[j] * x[n_m + j]), n_m = floor(m*D/I), p_m = (m*D) mod I
+ *                     (filter/polyphase_fir.c:184-227, filter/utils.c:46-116); also keeps the <= M input samples per
+ *                     channel the next feed still needs.
+ *   pocsag_kernel     one WARP per channel over the resampled 38400 Hz stream: optional DC blocker
+ *                     (filter/dc_blocker.h:72-92), slicer, 3-rate eye sync detector with the lanes across the eye-phase
+ *                     registers, 16-word batch sampled 32 bits per ballot, BCH(31,21) correction, address / alpha /
+ *                     numeric assembly (pager/pager_pocsag.c:82-543, pager/bch_code.c:307-398).  Messages are queued per
+ *                     channel for the host callbacks.
  *   flex_kernel       one thread per channel over the resampled 16000 Hz stream: optional DC blocker, Sync 1
  *                     (10-phase bit-sync search, A / B / inverted A, FIW), slicer training, Sync 2, 4 codings
  *                     (1600/2, 3200/2, 3200/4, 6400/4), block de-interleave into up to 4 phases, BCH + checksum,
  *                     BIW / address / vector walk, alphanumeric / numeric / tone / SIV assembly
  *                     (pager/pager_flex.c, whole file).
- *   pcm_carry_kernel  keeps the <= M input samples per channel the next feed still needs.
+ *   pcm_carry_kernel  (negated / channel-gathered) copy of a feed for banks without a resampler.
  *
  * All arithmetic is integer/bitwise and reproduces the reference bit for bit, including its quirks:
  * LSB-first batch words (`bit << bit_count`, count masked to 5 bits as x86 does), the bit-reversed idle
@@ -119,22 +121,40 @@ __device__ __forceinline__ int pcm_at(const InPcm &w, int c, long long i)
     return w.invert ? (int)(short)(-v) : v;
 }
 
-__global__ void resample_kernel(InPcm in, unsigned long long base, const short *__restrict__ phase_filters, int M,
+/* One block = 256 consecutive outputs of one channel.  The input window they need ([n_first, n_last + M), carry and
+ * fresh part resolved once) is staged in shared memory, then every thread runs its own phase filter over it.  The last
+ * block column (blockIdx.x == gridDim.x - 1) instead keeps the input samples the next feed still needs. */
+constexpr int RS_THREADS = 256;
+
+__global__ void __launch_bounds__(RS_THREADS) resample_kernel(InPcm in, unsigned long long base, const short *__restrict__ phase_filters, int M,
                                 unsigned interp, unsigned decim, unsigned long long m0, unsigned nr_out,
-                                short *__restrict__ out, long long out_pitch)
+                                short *__restrict__ out, long long out_pitch, int span_cap,
+                                long long keep_from, short *__restrict__ keep_dst, long long keep_pitch, int keep_n)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ short win[];
     const int c = blockIdx.y;
-    if (i >= nr_out) return;
-    const unsigned long long m = m0 + i;
-    const unsigned long long adv = m * decim;
+    if (blockIdx.x == gridDim.x - 1) {              /* the carry for the next feed */
+        for (int i = threadIdx.x; i < keep_n; i += RS_THREADS) keep_dst[(size_t)c * keep_pitch + i] = (short)pcm_at(in, c, keep_from + i);
+        return;
+    }
+    const unsigned i0 = blockIdx.x * RS_THREADS;
+    const unsigned cnt = min((unsigned)RS_THREADS, nr_out - i0);
+    const unsigned long long n_first = (m0 + i0) * decim / interp;
+    const unsigned long long n_last = (m0 + i0 + cnt - 1) * decim / interp;
+    const int span = (int)(n_last - n_first) + M;
+    const long long off0 = (long long)(n_first - base);
+    for (int i = threadIdx.x; i < span && i < span_cap; i += RS_THREADS) win[i] = (short)pcm_at(in, c, off0 + i);
+    __syncthreads();
+    if (threadIdx.x >= cnt) return;
+    const unsigned long long adv = (m0 + i0 + threadIdx.x) * decim;
     const unsigned long long n_m = adv / interp;
     const unsigned p = (unsigned)(adv % interp);
     const short *h = phase_filters + (size_t)p * M;
-    const long long off = (long long)(n_m - base);
+    const short *x = win + (int)(n_m - n_first);
     int acc = 0;
-    for (int j = 0; j < M; j++) acc += pcm_at(in, c, off + j) * (int)h[j];
-    out[(size_t)c * out_pitch + i] = (short)rq14(acc);
+#pragma unroll 4
+    for (int j = 0; j < M; j++) acc += (int)x[j] * (int)h[j];
+    out[(size_t)c * out_pitch + i0 + threadIdx.x] = (short)rq14(acc);
 }
 
 __global__ void pcm_carry_kernel(InPcm in, long long from, short *__restrict__ dst, long long dst_pitch, int n)
@@ -192,18 +212,6 @@ __device__ void msg_reset(PocsagState &p)
     p.vb_alpha = p.vb_numeric = 0;
     p.seen_nonprint = 0; p.score = 0;
     p.msg_type = MT_NONE; p.function = 0;
-}
-
-__device__ void batch_reset(PocsagState &p)
-{
-    for (int i = 0; i < 16; i++) p.batch[i] = 0;
-    p.b_word = p.b_word_bit = p.b_skip = p.b_bits = 0;
-}
-
-__device__ void eyes_reset(PocsagState &p)
-{
-    for (int i = 0; i < 75 + 32 + 16; i++) p.eye_reg[i] = 0;
-    for (int i = 0; i < 3; i++) { p.eye_cur[i] = 0; p.eye_matches[i] = 0; }
 }
 
 /* pager/pager_pocsag.c:242-297 */
@@ -285,101 +293,199 @@ __device__ void process_batch(PocsagState &p, char *alpha, char *numeric, const 
 
 __device__ __forceinline__ bool sync_ok(uint32_t w) { return __popc(w ^ POCSAG_SYNC) <= 4; }
 
-/* pager/pager_pocsag.c:82-117 */
-__device__ __forceinline__ void eye_on_sample(PocsagState &p, int which, int reg_base, uint32_t spb, uint32_t baud, uint32_t bit)
+/* ---- POCSAG decoder, one WARP per channel (pager/pager_pocsag.c:434-543 and :82-117) --------------------------------
+ * The reference walks the 38400 Hz stream sample by sample through a 4-state machine.  The same machine, event driven:
+ *   pass 1  the optional DC blocker (a sequential IIR, every lane computes the identical recurrence so nobody diverges)
+ *           and the slicer: sign bits of the whole feed, 32 samples per ballot, into a per-channel bit array;
+ *   pass 2  SEARCH: 32 samples per step -- lane l shifts sample l's bit into ITS eye-phase register of each of the three
+ *           rates (75 + 32 + 16 registers, eye_cur[] picks the phase exactly like the reference; the 16 registers of the
+ *           2400-baud detector are hit twice per step, lanes 0-15 then 16-31) and tests it against the sync word; the
+ *           three match masks are then scanned in sample order for the run-length logic (in noise: one iteration);
+ *           BATCH / SYNCWORD: the next 32 bits are sampled every sample_skip-th sample -- lane j fetches bit j of the
+ *           word straight from the bit array, one ballot assembles it (LSB first for batch words, MSB first for the
+ *           sync word, like the reference); BCH, address / message assembly and delivery run on lane 0.
+ * Registers updated past a detection inside a SEARCH step are never looked at again: the eye state is only read in
+ * SEARCH, and every return to SEARCH goes through eyes_reset (:524-527). */
+constexpr int PW_WARPS = 4;                 /* channels (warps) per block */
+
+__device__ __forceinline__ unsigned bit_at(const unsigned *__restrict__ bits, unsigned long long pos)
 {
-    uint32_t &r = p.eye_reg[reg_base + p.eye_cur[which]];
-    r = (r << 1) | bit;
-    if (sync_ok(r)) {
-        p.eye_matches[which]++;
-    } else if (p.eye_matches[which] > spb / 2) {
-        p.sample_skip = spb;
-        p.baud = baud;
-        batch_reset(p);
-        p.b_skip = (p.eye_matches[which] / 2) & 0xffffu;
-        p.state = ST_SYNCHRONIZED;
-    } else {
-        p.eye_matches[which] = 0;
-    }
-    p.eye_cur[which] = (p.eye_cur[which] + 1) % spb;
+    return (bits[pos >> 5] >> (pos & 31)) & 1u;
 }
 
-__global__ void pocsag_kernel(PocsagState *__restrict__ states, char *__restrict__ text, int nr_channels,
-                              short *__restrict__ pcm, long long pitch, unsigned n, MsgSink sink, int use_dc, int dc_p)
+/* samples until (and including) the next one a bit is taken from: skip counts up modulo 2^16 and fires on == sample_skip */
+__device__ __forceinline__ unsigned until_sampling(unsigned sample_skip, unsigned skip)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nr_channels) return;
-    PocsagState &g = states[c];
-    PocsagState p = g;                      /* working copy (registers / local memory) */
+    const unsigned k = (sample_skip - skip) & 0xffffu;
+    return k ? k : 65536u;
+}
+
+__global__ void __launch_bounds__(32 * PW_WARPS) pocsag_kernel(PocsagState *__restrict__ states, char *__restrict__ text, int nr_channels,
+                              short *__restrict__ pcm, long long pitch, unsigned n, unsigned *__restrict__ bits_all, unsigned bits_pitch,
+                              MsgSink sink, int use_dc, int dc_p)
+{
+    __shared__ PocsagState sst[PW_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int c = blockIdx.x * PW_WARPS + wib;
+    if (c >= nr_channels) return;                                   /* whole warps leave: no block-wide barrier below */
+    PocsagState &S = sst[wib];
+    {
+        const unsigned *src = reinterpret_cast<const unsigned *>(states + c);
+        unsigned *dst = reinterpret_cast<unsigned *>(&S);
+        for (int i = lane; i < (int)(sizeof(PocsagState) / 4); i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
     char *alpha = text + (size_t)c * 1024, *numeric = alpha + 512;   /* message_alpha[512], message_numeric[512] */
     short *x = pcm + (size_t)c * pitch;
+    unsigned *bits = bits_all + (size_t)c * bits_pitch;
 
-    for (unsigned i = 0; i < n; i++) {
-        int sample = x[i];
-        if (use_dc) {                       /* filter/dc_blocker.h:79-88 */
-            p.dc_acc -= p.dc_x;
-            p.dc_x = sample << 14;
-            p.dc_acc += p.dc_x - dc_p * p.dc_y;
-            p.dc_y = p.dc_acc >> 14;
-            sample = (int)(short)p.dc_y;
-            x[i] = (short)sample;
+    /* ---- pass 1: DC blocker (filter/dc_blocker.h:79-88) and slicer ---- */
+    {
+        int dc_x = S.dc_x, dc_y = S.dc_y, dc_acc = S.dc_acc;
+        for (unsigned g0 = 0; g0 < n; g0 += 32) {
+            const unsigned idx = g0 + lane;
+            int v = idx < n ? (int)x[idx] : 0;
+            if (use_dc) {
+                const unsigned cnt = min(32u, n - g0);
+                int mine = v;
+                for (unsigned t = 0; t < cnt; t++) {
+                    const int sample = __shfl_sync(0xffffffffu, v, t);
+                    dc_acc -= dc_x;
+                    dc_x = sample << 14;
+                    dc_acc += dc_x - dc_p * dc_y;
+                    dc_y = dc_acc >> 14;
+                    if ((unsigned)lane == t) mine = (int)(short)dc_y;
+                }
+                v = mine;
+                if (idx < n) x[idx] = (short)v;
+            }
+            const unsigned w = __ballot_sync(0xffffffffu, idx < n && v < 0);
+            if (lane == 0) bits[g0 >> 5] = w;
         }
-        const uint32_t bit = sample < 0 ? 1u : 0u;
-        /* one sample through the 4-state machine (pager/pager_pocsag.c:434-543) */
-        if (p.state == ST_SYNCHRONIZED) p.state = ST_BATCH;
-        switch (p.state) {
-        case ST_SEARCH:
-            eye_on_sample(p, 0, 0, 75, 512, bit);
-            eye_on_sample(p, 1, 75, 32, 1200, bit);
-            eye_on_sample(p, 2, 75 + 32, 16, 2400, bit);
-            break;
-        case ST_BATCH:
-            p.b_skip = (p.b_skip + 1) & 0xffffu;
-            if (p.b_skip == p.sample_skip) {
-                p.batch[p.b_word] |= bit << (p.b_bits & 31);
-                p.b_word_bit++; p.b_bits = (p.b_bits + 1) & 0xffffu; p.b_skip = 0;
-                if (p.b_word_bit == 32) {
-                    p.b_word_bit = 0;
-                    if (++p.b_word == 16) {
-                        process_batch(p, alpha, numeric, sink, c);
-                        p.state = ST_SYNCWORD;
-                        p.b_word = 0;
-                        p.s_skip = 0; p.s_bits = 0; p.s_word = 0;
+        if (lane == 0) { bits[(n + 31) >> 5] = 0; S.dc_x = dc_x; S.dc_y = dc_y; S.dc_acc = dc_acc; }
+        __syncwarp();
+    }
+
+    /* ---- pass 2: the state machine ---- */
+    const unsigned spbs[3] = { 75, 32, 16 }, bauds[3] = { 512, 1200, 2400 }, bases[3] = { 0, 75, 75 + 32 };
+    unsigned i = 0;
+    if (S.state == ST_SYNCHRONIZED) { if (lane == 0) S.state = ST_BATCH; __syncwarp(); }
+    while (i < n) {
+        const int state = S.state;
+        if (state == ST_SEARCH) {
+            const unsigned cnt = min(32u, n - i);
+            const unsigned word = __funnelshift_r(bits[i >> 5], bits[(i >> 5) + 1], i & 31);
+            const unsigned bit = (word >> lane) & 1u;
+            unsigned mask[3], matches[3], cur[3];
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+                const unsigned spb = spbs[b];
+                cur[b] = S.eye_cur[b]; matches[b] = S.eye_matches[b];
+                bool m = false;
+                /* spb = 16: two samples of a step share a register -- lanes 0-15 first, then 16-31 */
+                for (int half = 0; half < (spb < 32 ? 2 : 1); half++) {
+                    const bool mine = (unsigned)lane < cnt && (spb >= 32 || (lane >> 4) == half);
+                    if (mine) {
+                        const unsigned ph = (cur[b] + (unsigned)lane) % spb;
+                        unsigned r = S.eye_reg[bases[b] + ph];
+                        r = (r << 1) | bit;
+                        S.eye_reg[bases[b] + ph] = r;
+                        m = sync_ok(r);
                     }
+                    __syncwarp();
+                }
+                mask[b] = __ballot_sync(0xffffffffu, m);
+            }
+            /* run-length logic in sample order; stops as soon as nothing more can happen in this step */
+            unsigned consumed = cnt;
+            bool trig = false;
+            unsigned t_skip = 0, t_baud = 0, t_bskip = 0;
+            for (unsigned sidx = 0; sidx < cnt; sidx++) {
+                if ((((mask[0] | mask[1] | mask[2]) >> sidx) == 0) && (matches[0] | matches[1] | matches[2]) == 0) break;
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    if ((mask[b] >> sidx) & 1u) matches[b]++;
+                    else if (matches[b] > spbs[b] / 2) { trig = true; t_skip = spbs[b]; t_baud = bauds[b]; t_bskip = (matches[b] / 2) & 0xffffu; }
+                    else matches[b] = 0;
+                }
+                if (trig) { consumed = sidx + 1; break; }
+            }
+            __syncwarp();
+            if (trig) {
+                if (lane < 16) S.batch[lane] = 0;                   /* batch_reset */
+                if (lane == 0) {
+                    S.sample_skip = t_skip; S.baud = t_baud;
+                    S.b_word = 0; S.b_word_bit = 0; S.b_bits = 0; S.b_skip = t_bskip;
+                    S.state = ST_BATCH;                             /* SYNCHRONIZED for the rest of this sample, BATCH from the next */
                 }
             }
-            break;
-        case ST_SYNCWORD:
-            p.s_skip = (p.s_skip + 1) & 0xffffu;
-            if (p.s_skip == p.sample_skip) {
-                p.s_skip = 0;
-                p.s_word = (p.s_word << 1) | bit;
-                if (++p.s_bits == 32) {
-                    if (!sync_ok(p.s_word)) {
-                        p.state = ST_SEARCH;
-                        p.sample_skip = 0;
-                        eyes_reset(p);
-                        deliver(p, alpha, numeric, sink, c);
-                    } else {
-                        p.state = ST_BATCH;
-                        batch_reset(p);
-                    }
-                }
+            if (lane < 3) { S.eye_cur[lane] = (cur[lane] + consumed) % spbs[lane]; S.eye_matches[lane] = matches[lane]; }
+            i += consumed;
+            __syncwarp();
+        } else {
+            /* BATCH (LSB-first into batch[]) or SYNCWORD (MSB-first into s_word): up to 32 bits, one every sample_skip samples */
+            const bool batch = state == ST_BATCH;
+            const unsigned spb = S.sample_skip;
+            const unsigned skip = batch ? S.b_skip : S.s_skip;
+            const unsigned have = batch ? S.b_word_bit : S.s_bits;
+            const unsigned long long first = (unsigned long long)i + until_sampling(spb, skip) - 1;
+            const unsigned long long pos = first + (unsigned long long)lane * spb;
+            const bool valid = (unsigned)lane < 32 - have && pos < n;
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            const unsigned w = __ballot_sync(0xffffffffu, valid && bit_at(bits, pos));
+            const unsigned nv = __popc(vmask);
+            if (nv == 0) {                                          /* the feed ends before the next bit */
+                if (lane == 0) { if (batch) S.b_skip = (skip + (n - i)) & 0xffffu; else S.s_skip = (skip + (n - i)) & 0xffffu; }
+                i = n;
+                __syncwarp();
+                continue;
             }
-            break;
+            const unsigned long long last = first + (unsigned long long)(nv - 1) * spb;
+            i = (unsigned)(last + 1);
+            if (batch) {
+                if (lane == 0) {
+                    S.batch[S.b_word] |= w << have;
+                    S.b_bits = (S.b_bits + nv) & 0xffffu; S.b_skip = 0;
+                    unsigned wb = have + nv;
+                    if (wb == 32) {
+                        wb = 0;
+                        if (++S.b_word == 16) {
+                            process_batch(S, alpha, numeric, sink, c);
+                            S.state = ST_SYNCWORD;
+                            S.b_word = 0;
+                            S.s_skip = 0; S.s_bits = 0; S.s_word = 0;
+                        }
+                    }
+                    S.b_word_bit = wb;
+                }
+            } else if (lane == 0) {
+                const unsigned msb_first = __brev(w) >> (32 - nv);  /* first sampled bit ends up highest */
+                S.s_word = (nv == 32) ? msb_first : ((S.s_word << nv) | msb_first);
+                S.s_skip = 0;
+                S.s_bits += nv;
+            }
+            __syncwarp();
+            if (!batch && S.s_bits == 32) {
+                const bool ok = sync_ok(S.s_word);
+                __syncwarp();
+                if (!ok) {
+                    for (int r = lane; r < 75 + 32 + 16; r += 32) S.eye_reg[r] = 0;     /* eyes_reset */
+                    if (lane < 3) { S.eye_cur[lane] = 0; S.eye_matches[lane] = 0; }
+                    if (lane == 0) { S.state = ST_SEARCH; S.sample_skip = 0; deliver(S, alpha, numeric, sink, c); }
+                } else {
+                    if (lane < 16) S.batch[lane] = 0;                                   /* batch_reset */
+                    if (lane == 0) { S.state = ST_BATCH; S.b_word = 0; S.b_word_bit = 0; S.b_skip = 0; S.b_bits = 0; }
+                }
+                __syncwarp();
+            }
         }
     }
-    /* write the scalar state and small arrays back; text buffers were written in place */
-    g.state = p.state; g.sample_skip = p.sample_skip; g.baud = p.baud;
-    g.b_skip = p.b_skip; g.b_word = p.b_word; g.b_word_bit = p.b_word_bit; g.b_bits = p.b_bits;
-    g.s_skip = p.s_skip; g.s_bits = p.s_bits; g.s_word = p.s_word;
-    for (int i = 0; i < 3; i++) { g.eye_cur[i] = p.eye_cur[i]; g.eye_matches[i] = p.eye_matches[i]; }
-    g.n_alpha = p.n_alpha; g.n_numeric = p.n_numeric; g.score = p.score; g.seen_nonprint = p.seen_nonprint;
-    g.capcode = p.capcode; g.w_alpha = p.w_alpha; g.w_numeric = p.w_numeric; g.vb_alpha = p.vb_alpha;
-    g.vb_numeric = p.vb_numeric; g.function = p.function; g.msg_type = p.msg_type;
-    g.dc_x = p.dc_x; g.dc_y = p.dc_y; g.dc_acc = p.dc_acc;
-    for (int i = 0; i < 16; i++) g.batch[i] = p.batch[i];
-    for (int i = 0; i < 75 + 32 + 16; i++) g.eye_reg[i] = p.eye_reg[i];
+    __syncwarp();
+    {
+        unsigned *dst = reinterpret_cast<unsigned *>(states + c);
+        const unsigned *src = reinterpret_cast<const unsigned *>(&S);
+        for (int k = lane; k < (int)(sizeof(PocsagState) / 4); k += 32) dst[k] = src[k];
+    }
 }
 
 
@@ -895,6 +1001,9 @@ struct gpupager {
     size_t last_out = 0;
     int decoder = GPUPAGER_DECODER_POCSAG;
     PocsagState *d_states = nullptr;
+    unsigned *d_bits = nullptr;         /* POCSAG: sliced bits of the current feed, [C][bits_pitch] words */
+    unsigned bits_pitch = 0;
+    int rs_span_cap = 0;                /* shorts of shared memory one resampler block stages */
     FlexState *d_fstates = nullptr;
     char *d_text = nullptr;
     uint32_t msg_cap = 32;
@@ -912,7 +1021,7 @@ static void pager_free(gpupager *h)
     cudaSetDevice(h->device);
     cudaFree(h->d_phase); cudaFree(h->d_carry[0]); cudaFree(h->d_carry[1]); cudaFree(h->d_stage); cudaFree(h->d_res);
     cudaFree(h->d_states); cudaFree(h->d_fstates); cudaFree(h->d_text); cudaFree(h->d_msgs); cudaFree(h->d_count); cudaFree(h->d_dropped);
-    cudaFree(h->d_map);
+    cudaFree(h->d_map); cudaFree(h->d_bits);
     if (h->ev_own) cudaEventDestroy(h->ev_own);
     if (h->ev_ext) cudaEventDestroy(h->ev_ext);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -976,6 +1085,14 @@ extern "C" int gpupager_create(gpupager_t **ph, const gpupager_cfg *cfg)
         h->carry_pitch = (long long)((m + 8 + 7) & ~(size_t)7);
         for (int i = 0; i < 2; i++) PFAIL(cudaMalloc(&h->d_carry[i], (size_t)C * h->carry_pitch * sizeof(short)));
         max_out = (h->max_feed + m) * h->interp / h->decim + 8;
+        /* input samples 256 consecutive outputs span, plus the filter length */
+        h->rs_span_cap = (int)((unsigned long long)RS_THREADS * h->decim / h->interp + m + 4);
+        if ((size_t)h->rs_span_cap * sizeof(short) > 200 * 1024) {
+            pager_free(h);
+            return perr(GPUPAGER_E_INVAL, "decimate / interpolate = %u / %u is too steep for the resampler tile", h->decim, h->interp);
+        }
+        if ((size_t)h->rs_span_cap * sizeof(short) > 48 * 1024)
+            PFAIL(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->rs_span_cap * (int)sizeof(short)));
     }
     h->res_pitch = (long long)((max_out + 63) & ~(size_t)63);
     PFAIL(cudaMalloc(&h->d_res, (size_t)C * h->res_pitch * sizeof(short)));
@@ -992,6 +1109,8 @@ extern "C" int gpupager_create(gpupager_t **ph, const gpupager_cfg *cfg)
         PFAIL(cudaMemset(h->d_states, 0, (size_t)C * sizeof(PocsagState)));
         PFAIL(cudaMalloc(&h->d_text, (size_t)C * 1024));
         PFAIL(cudaMemset(h->d_text, 0, (size_t)C * 1024));
+        h->bits_pitch = (unsigned)(h->res_pitch / 32 + 2);
+        PFAIL(cudaMalloc(&h->d_bits, (size_t)C * h->bits_pitch * sizeof(unsigned)));
     }
     h->msg_cap = 32 + (uint32_t)(max_out / 1000);       /* shortest message: 2 codewords x 16 samples/bit */
     if (h->decoder == GPUPAGER_DECODER_FLEX)
@@ -1048,27 +1167,22 @@ static int pager_run(gpupager *h, const short *d_pcm, size_t pitch, size_t n, cu
         }
         const unsigned long long nr_out = m_end - h->m_next;
         if (nr_out > (unsigned long long)h->res_pitch) return perr(GPUPAGER_E_INVAL, "feed too large for the output buffer");
-        if (nr_out) {
-            dim3 grid((unsigned)((nr_out + 255) / 256), C);
-            resample_kernel<<<grid, 256, 0, st>>>(in, h->in_base, h->d_phase, h->M, h->interp, h->decim, h->m_next,
-                                                  (unsigned)nr_out, h->d_res, h->res_pitch);
+        /* keep input from n_next on (the resampler kernel's last block column saves it) */
+        unsigned long long n_next = m_end * h->decim / h->interp;
+        if (n_next > total) n_next = total;
+        if (n_next < h->in_base) n_next = h->in_base;
+        const long long keep = (long long)(total - n_next);
+        if (keep > h->carry_pitch) return perr(GPUPAGER_E_INVAL, "internal: carry %lld exceeds capacity", keep);
+        {
+            dim3 grid((unsigned)((nr_out + RS_THREADS - 1) / RS_THREADS) + 1, C);
+            resample_kernel<<<grid, RS_THREADS, h->rs_span_cap * sizeof(short), st>>>(
+                in, h->in_base, h->d_phase, h->M, h->interp, h->decim, h->m_next, (unsigned)nr_out, h->d_res, h->res_pitch,
+                h->rs_span_cap, (long long)(n_next - h->in_base), h->d_carry[h->pp ^ 1], h->carry_pitch, (int)keep);
             h->launches++;
             PCUDA(cudaGetLastError());
         }
         h->m_next = m_end;
         h->total_in = total;
-        /* keep input from n_next on */
-        unsigned long long n_next = h->m_next * h->decim / h->interp;
-        if (n_next > total) n_next = total;
-        if (n_next < h->in_base) n_next = h->in_base;
-        const long long keep = (long long)(total - n_next);
-        if (keep > h->carry_pitch) return perr(GPUPAGER_E_INVAL, "internal: carry %lld exceeds capacity", keep);
-        if (keep > 0) {
-            dim3 grid((unsigned)((keep + 63) / 64), C);
-            pcm_carry_kernel<<<grid, 64, 0, st>>>(in, (long long)(n_next - h->in_base), h->d_carry[h->pp ^ 1], h->carry_pitch, (int)keep);
-            h->launches++;
-            PCUDA(cudaGetLastError());
-        }
         h->pp ^= 1;
         h->carry_len = keep;
         h->in_base = n_next;
@@ -1099,8 +1213,9 @@ static int pager_run(gpupager *h, const short *d_pcm, size_t pitch, size_t n, cu
             flex_kernel<<<(C + 31) / 32, 32, 0, st>>>(h->d_fstates, C, const_cast<short *>(dec_in), dec_pitch, nr_dec, sink,
                                                       (h->flags & GPUPAGER_F_DC_BLOCK) ? 1 : 0, h->dc_p);
         else
-            pocsag_kernel<<<(C + 31) / 32, 32, 0, st>>>(h->d_states, h->d_text, C, const_cast<short *>(dec_in), dec_pitch, nr_dec, sink,
-                                                        (h->flags & GPUPAGER_F_DC_BLOCK) ? 1 : 0, h->dc_p);
+            pocsag_kernel<<<(C + PW_WARPS - 1) / PW_WARPS, 32 * PW_WARPS, 0, st>>>(h->d_states, h->d_text, C, const_cast<short *>(dec_in), dec_pitch,
+                                                                                    nr_dec, h->d_bits, h->bits_pitch, sink,
+                                                                                    (h->flags & GPUPAGER_F_DC_BLOCK) ? 1 : 0, h->dc_p);
         h->launches++;
         PCUDA(cudaGetLastError());
     }

@@ -52,9 +52,37 @@ __global__ void atan_selftest_kernel(uint64_t seed, uint64_t per_thread, const f
     uint64_t s = seed + 0x1234567ull * (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x);
     ap.use_fma = FMA ? 1 : 0;
     unsigned long long bad_atan = 0, bad_pcm = 0, exact = 0;
+    int prev_im = 0, prev_re = 0;
+    const uint32_t tab_biased = tab_smem - 0x4B000000u * 8u;
     for (uint64_t i = 0; i < per_thread; i++) {
         int s_im, s_re;
         draw_pair(s, s_im, s_re);
+        /* v3 (packed pairs, what the fused kernel runs): this operand pair rides next to the previous one, in both halves */
+        {
+            const float want[2] = { fast_atan2f_dev((float)prev_im, (float)prev_re, tab, ap), fast_atan2f_dev((float)s_im, (float)s_re, tab, ap) };
+            const int pi_[2] = { (i & 1) ? prev_im : s_im, (i & 1) ? s_im : prev_im };
+            const int pr_[2] = { (i & 1) ? prev_re : s_re, (i & 1) ? s_re : prev_re };
+            Atan2Pair ap2;
+            float ex[2], ey[2], phi[2];
+            atan2p_stage1(pi_[0], pr_[0], pi_[1], pr_[1], ap2);
+            atan2p_stage2(ap2, tab_biased, 8u, ex, ey);
+            atan2p_stage3<FMA>(pi_[0], pr_[0], pi_[1], pr_[1], ap2, ex, ey, ap.z_small_thr, phi[0], phi[1]);
+            float margin = 1.0f;
+            int pcm[2];
+            pcm_from_phi_pair(phi[0], phi[1], margin, pcm[0], pcm[1]);
+            for (int k = 0; k < 2; k++) {
+                const float w = want[(i & 1) ? k : 1 - k];
+                if (__float_as_uint(w) != __float_as_uint(phi[k]) && !(w == 0.0f && phi[k] == 0.0f)) {
+                    if (atomicAdd(&out[3], 1ull) == 0) { out[4] = (unsigned)pi_[k]; out[5] = (unsigned)pr_[k]; out[6] = __float_as_uint(w); out[7] = __float_as_uint(phi[k]); }
+                    bad_atan++;
+                }
+                const double qq = __dmul_rn(__ddiv_rn((double)w, 3.14159265358979323846), 16384.0);
+                const int pw = __float2int_rz(__double2float_rn(qq));
+                const int got = (margin < 0.0f) ? pcm_from_phi_exact(__fmul_rn(phi[k], 16384.0f)) : pcm[k];
+                if (got != pw) bad_pcm++;
+            }
+            prev_im = s_im; prev_re = s_re;
+        }
         const float ref = fast_atan2f_dev((float)s_im, (float)s_re, tab, ap);
         const float v2 = fast_atan2f_v2<FMA>(s_im, s_re, tab_smem, ap.z_small_thr);
         if (__float_as_uint(ref) != __float_as_uint(v2) && !(ref == 0.0f && v2 == 0.0f)) {
@@ -91,6 +119,17 @@ __global__ void pcm_selftest_kernel(uint32_t first, uint64_t count, unsigned lon
         if (pcm != pcm_want) {
             if (atomicAdd(&out[3], 1ull) == 0) { out[4] = bits; out[5] = (unsigned)pcm_want; out[6] = (unsigned)pcm; }
             bad++;
+        }
+        /* v3: the packed form, this angle in one half and its negation in the other */
+        {
+            float m2 = 1.0f;
+            int p0, p1;
+            pcm_from_phi_pair(phi, -phi, m2, p0, p1);
+            if (m2 < 0.0f) { p0 = pcm_from_phi_exact(__fmul_rn(phi, 16384.0f)); p1 = pcm_from_phi_exact(__fmul_rn(-phi, 16384.0f)); }
+            if (p0 != pcm_want || p1 != -pcm_want) {
+                if (atomicAdd(&out[3], 1ull) == 0) { out[4] = bits; out[5] = (unsigned)pcm_want; out[6] = (unsigned)p0; out[7] = (unsigned)p1; }
+                bad++;
+            }
         }
     }
     atomicAdd(&out[1], bad);

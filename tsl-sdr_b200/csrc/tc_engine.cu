@@ -35,10 +35,6 @@
 #include "tc_engine.cuh"
 #include "tc_ptx.cuh"
 
-#ifndef TC_DIAG
-#define TC_DIAG 0       /* diagnostics builds only (tools/gpujob_diag.sh): 1 = no PCM scaling, 2 = no arctangent, 4 = no derotator */
-#endif
-
 #include <cstdio>
 #include <cstring>
 #include <type_traits>
@@ -60,6 +56,9 @@ constexpr int MMA_WARPS = 2;            /* MMA issuers (2 = each owns a disjoint
 constexpr int MMA_WARP = EPI_WARPS + XF_WARPS;      /* warp index of the first MMA issuer */
 constexpr int TC_THREADS = 32 * (XF_WARPS + MMA_WARPS + EPI_WARPS);
 constexpr int NB_MAX = 4, NT_MAX = 3;
+/* nanoseconds between polls of a role's barrier wait (measured on B200: shorter intervals spend issue slots the epilogue
+ * needs, longer ones add latency to the hand-offs; hardware-suspended try_wait was no faster) */
+constexpr uint32_t SLEEP_EPI = 200, SLEEP_XF = 1000, SLEEP_MMA = 100;
 
 /* ---------------------------------------------------------------------------------------------- */
 struct TcKernelParams {
@@ -85,17 +84,8 @@ struct TcKernelParams {
     int C, G, Kp, Q, R;
     int nb_stages, prog_len, prog_split, prog_regular;
     int atan_copies;        /* interleaved copies of the arctangent table in shared memory: 16 or 1 */
-    int rot_lt;             /* ROT_TAB: entries per channel of the shared-memory derotator table */
-    float inv_nslab;
     uint32_t a_group_bytes, b_stage_bytes;
     AtanParams atan;
-    long long *dbg;         /* optional per-role clock stamps of CTA 0 (bench diagnostics) */
-    int dbg_flags;          /* diagnostics only: 1 = skip the epilogue arithmetic, 2 = skip the transform */
-    uint32_t sleep_epi, sleep_xf, sleep_mma;    /* nanoseconds between polls of a role's barrier wait */
-    int tune;               /* experiments (GPUCHAN_TC_TUNE): 1 = epilogue waits for t_full with a "suspended" try_wait instead of
-                               nanosleep polling (ncu: NANOSLEEP.SYNCS returns at once, the loop spins: 19 % of all issued
-                               instructions), 2 = same for the transform's b_empty wait, 16 = same for the MMA warps, 4 = generic (select-based) transform loads,
-                               8 = derotator phases from a shared-memory table (ROT_TAB), 32 = lane-loop MMA issue only */
     TcMma prog[TC_PROG_MAX];
 };
 
@@ -132,10 +122,7 @@ __device__ __forceinline__ void split_store(const uint32_t (&w)[8], uint8_t *hi_
 }
 
 
-/* ROT_TAB: steady state with short derotator cycles -- every channel's limit cycle (pre-scaled by 4, unrolled
- * 2 * TC_STEP + 1 entries past its period) sits in shared memory and the epilogue reads the phases instead of
- * stepping the recurrence. */
-template <int MODE, bool KEEP_IQ, bool FMA, bool ROT_TAB>
+template <int MODE, bool KEEP_IQ, bool FMA>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_constant__ TcKernelParams p)
 {
     constexpr int ACCS = (MODE == TC_MODE_SUM) ? 2 : 3;
@@ -148,12 +135,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
 
     uint8_t *sA = smem;                                         /* [a_chunks][2 slabs][128][16] */
     uint8_t *sB = smem + p.a_group_bytes;                       /* [NB stages][2 planes][nslab][R][16] */
-    int2 *sR = reinterpret_cast<int2 *>(sB + (size_t)p.nb_stages * p.b_stage_bytes);    /* [TC_CH][rot_lt + 1] 4 * rot (ROT_TAB) */
     /* arctangent table, entry-major with atan_copies (16 or 1) interleaved copies: entry i of copy c sits at
      * (i * copies + c) * 8 bytes, so that with 16 copies lane l (copy l & 15) always reads bank pair l & 15 -- every
      * table load is two conflict-free wavefronts.  (One shared copy cost 12.8 wavefronts per load on average: the
      * look-ups alone kept the shared-memory data pipe 30 % busy next to the tensor core's operand reads.) */
-    float2 *sT = reinterpret_cast<float2 *>(reinterpret_cast<uint8_t *>(sR) + (ROT_TAB ? (size_t)TC_CH * (p.rot_lt + 1) * sizeof(int2) : 0));
+    float2 *sT = reinterpret_cast<float2 *>(sB + (size_t)p.nb_stages * p.b_stage_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);       /* same value, but provably warp-uniform for the compiler */
     const int nslab = p.Kp >> 4;
@@ -188,18 +174,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         for (uint32_t i = tid; i < p.a_group_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
         for (int i = tid; i < 256 * p.atan_copies; i += TC_THREADS) sT[i] = p.atan_tab[i / p.atan_copies];
         for (int i = tid; i < p.prog_len; i += TC_THREADS) prog_s[i] = p.prog[i];
-        if (ROT_TAB) {
-            const int lt = p.rot_lt;                            /* power of two >= longest period + TC_STEP + 1 */
-            for (int i = tid; i < TC_CH * lt; i += TC_THREADS) {
-                const int chn = i / lt, j = i - chn * lt, cc = g * TC_CH + chn;
-                int2 v = make_int2(0, 0);
-                if (cc < p.C) {
-                    const int w = __ldg(p.cyc + (size_t)cc * p.cyc_pitch + (uint32_t)j % __ldg(p.lambda + cc));
-                    v = make_int2(4 * lo16(w), 4 * hi16(w));
-                }
-                sR[chn * (lt + 1) + j] = v;                     /* odd row pitch: the 16 channels of a half-warp hit 16 bank pairs */
-            }
-        }
     }
     if (tid == 0) {
         for (int s = 0; s < NB_MAX; s++) { ptx::mbar_init(&b_full[s], (uint32_t)((XF_WARPS - s + p.nb_stages - 1) / p.nb_stages)); ptx::mbar_init(&b_empty[s], MMA_WARPS); }
@@ -212,7 +186,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-#define DBG(role, it, slot) do { if (p.dbg && blockIdx.x == 0 && (it) < 32) p.dbg[((role) * 32 + (it)) * 8 + (slot)] = clock64(); } while (0)
 
     if (warp_u >= XF_WARP0 && warp_u < XF_WARP0 + XF_WARPS) {
         const int xall = tid - 32 * XF_WARP0;       /* 0 .. XF_THREADS-1 */
@@ -231,20 +204,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         const int items = p.R * nslab;
         const uint32_t slab_bytes = (uint32_t)p.R * 16;
         if (xt == 0) prefetch_tile(tile0 + grp + NB);
-        const bool xstamp = xall == 0;
         for (int it = grp; it < my_tiles; it += NB) {
             const int s = grp, ph = (it / NB) & 1;
-            if (xstamp) DBG(0, it / NB, 0);
             if (xt == 0) prefetch_tile(tile0 + it + 2 * NB);
-            if (p.tune & 2) ptx::mbar_wait_sleep(&b_empty[s], ph ^ 1, 100000);
-            else ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, p.sleep_xf);
-            if (xstamp) DBG(0, it / NB, 1);
+            ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, SLEEP_XF);
             uint8_t *dst = sB + (size_t)s * p.b_stage_bytes;
             const long long row_base = (long long)TC_OUT * (tile0 + it) - TC_LEAD;
             const long long s_first = row_base * (long long)p.D;
             const long long s_last = s_first + (long long)(p.R - 1) * p.D + 8 * nslab + 12;     /* one past the furthest word read */
-            if (p.dbg_flags & 2) {
-            } else if (s_first >= p.in.carry_len + 4 && s_last <= p.in.total) {
+            if (s_first >= p.in.carry_len + 4 && s_last <= p.in.total) {
                 /* a thread keeps one slab column j and walks down the rows: addresses advance by constants, and the
                  * loads of consecutive rows are independent, so several stay in flight */
                 const int *base = p.in.fresh + (s_first - p.in.carry_len);
@@ -254,7 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                 uint8_t *d_hi = dst + (size_t)j * slab_bytes + rl * 16;
                 const size_t lo_off = (size_t)nslab * slab_bytes;
                 if (rl >= row_lanes) {
-                } else if ((p.D & 3) == 0 && !(p.tune & 4)) {
+                } else if ((p.D & 3) == 0) {
                     /* rows start a multiple of 4 samples apart: every 8-sample item of the tile has the same
                      * misalignment o_tile against 16 bytes, so the word rotation is resolved at compile time */
                     const uint4 *al = reinterpret_cast<const uint4 *>(reinterpret_cast<uintptr_t>(base) & ~(uintptr_t)15) + ((rl * p.D) >> 2) + 2 * j;
@@ -303,7 +271,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             ptx::fence_proxy_async();       /* generic-proxy stores -> visible to the tensor core's async proxy */
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&b_full[s]);
-            if (xstamp) DBG(0, it / NB, 2);
         }
         /* keep the tail of the window the next submit still needs (fewer than T samples) */
         if (blockIdx.x == 0 && p.carry_out)
@@ -315,7 +282,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
          * Within a warp the first MMA into an accumulator (accumulate = 0) goes out before the others; beyond that
          * the order of accumulation does not matter. */
         const int mw = warp_u - MMA_WARP;
-        const bool leader = lane == 0 && mw == 0;
         const int i0 = (MMA_WARPS == 1 || mw == 0) ? 0 : p.prog_split, i1 = (MMA_WARPS == 1 || mw != 0) ? p.prog_len : p.prog_split;
         const int n_mine = i1 - i0;
         const uint32_t a_base = ptx::smem_u32(sA) >> 4, b_base0 = ptx::smem_u32(sB) >> 4;
@@ -348,11 +314,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             if (NFIX == 0 && have0) m0 = prog_s[i0 + lane];
             int sb = 0, phb = 0, st = 0, pht = 0;
             for (int it = 0; it < my_tiles; it++) {
-                if (leader) DBG(1, it, 0);
-                if (p.tune & 16) { ptx::mbar_wait_sleep(&b_full[sb], phb, 200000); } else ptx::mbar_wait_backoff(&b_full[sb], phb, p.sleep_mma);
-                if (leader) DBG(1, it, 1);
-                if (p.tune & 16) { ptx::mbar_wait_sleep(&t_empty[st], pht ^ 1, 200000); } else ptx::mbar_wait_backoff(&t_empty[st], pht ^ 1, p.sleep_mma);
-                if (leader) DBG(1, it, 2);
+                ptx::mbar_wait_backoff(&b_full[sb], phb, SLEEP_MMA);
+                ptx::mbar_wait_backoff(&t_empty[st], pht ^ 1, SLEEP_MMA);
                 ptx::tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)st * STAGE_COLS;
                 const uint32_t b_base = b_base0 + (((uint32_t)sb * p.b_stage_bytes) >> 4);
@@ -392,13 +355,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                     ptx::mma_commit(&b_empty[sb]);      /* smem stage may be refilled once these MMAs have read it */
                     ptx::mma_commit(&t_full[st]);       /* accumulators complete */
                 }
-                if (leader) DBG(1, it, 4);
                 __syncwarp();
                 if (++sb == NB) { sb = 0; phb ^= 1; }
                 if (++st == NT) { st = 0; pht ^= 1; }
             }
         };
-        if ((p.tune & 32) || !p.prog_regular) mma_role(std::integral_constant<int, 0>{});
+        if (!p.prog_regular) mma_role(std::integral_constant<int, 0>{});
         else if (n_mine <= 12) mma_role(std::integral_constant<int, 12>{});
         else if (n_mine <= 24) mma_role(std::integral_constant<int, 24>{});
         else mma_role(std::integral_constant<int, 0>{});
@@ -446,7 +408,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         /* derotator phase word of tile `it` of this CTA: the phase of the output before my first block (of output 0
          * itself for the very first block of the stream segment); fetched one tile ahead so that its latency hides
          * behind the arithmetic of the current tile */
-        const int2 *const rrow = sR + (size_t)ch * (p.rot_lt + 1);    /* ROT_TAB: this channel's row of the phase table */
         auto phase_word = [&](int it) -> int {
             if (!live) return 0;
             const int tile = tile0 + it;
@@ -456,23 +417,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                 uint32_t ix = tph;
                 tph += tstep;
                 if (tph >= lam) tph -= lam;
-                if (ROT_TAB) return (int)ix;                    /* table index of the phase of output kfirst - 1 */
                 if (tile == 0 && blk0 == 0) { ix++; if (ix == lam) ix = 0; }
                 return __ldg(tab + ix);
             }
             return __ldg(p.ckpt + ((size_t)tile * TC_SUB + blk0) * p.C + c);
         };
         int cwk_next = set < my_tiles ? phase_word(set) : 0;
-        const bool stamp = tid == 0;
 
         for (int it = set; it < my_tiles; it += 2) {
             const int tile = tile0 + it;
             const int st = it % NT, pht = (it / NT) & 1;
             const int cwk = cwk_next;
-            if (stamp) DBG(2, it >> 1, 0);
-            if (p.tune & 1) ptx::mbar_wait_sleep(&t_full[st], pht, 100000);
-            else ptx::mbar_wait_backoff(&t_full[st], pht, p.sleep_epi);
-            if (stamp) DBG(2, it >> 1, 1);
+            ptx::mbar_wait_backoff(&t_full[st], pht, SLEEP_EPI);
             ptx::tc_fence_after();
             const uint32_t col0 = tmem_base + (uint32_t)st * STAGE_COLS + TC_LEAD + 32 * half;
             /* limb weights: SUM (2^8, 1), RADIX (2^16, 2^8, 1); times 4 and + 0x8000 for the rounding shift */
@@ -501,7 +457,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             };
 
             int r_re = lo16(cwk), r_im = hi16(cwk);
-            const int2 *rp = rrow + (ROT_TAB ? cwk : 0);    /* rp[0] = 4 * phase of output kfirst - 1, rp[1 + u] of output kfirst + u */
             int p_re = 0, p_im = 0;
 #pragma unroll 1
             for (int b = 0; b < 2; b++) {
@@ -519,15 +474,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                         ptx::tmem_ld1_split16(col0 - 1 + lane_im + 2 * TC_ACC_STRIDE, l2i);
                     }
                     drain8(col0, x_re, x_im);
-                    if (stamp) DBG(2, it >> 1, 2);
                     if (it + 2 < my_tiles) cwk_next = phase_word(it + 2);
                     if (kfirst == 0) {
                         /* very first output of the submit: y[-1] is carried state; the phase word = phase of output 0 */
                         const int lw = live ? __ldg(p.last_in + c) : 0;
                         p_re = lo16(lw); p_im = hi16(lw);
-                    } else if (ROT_TAB) {
-                        const int2 r4 = rp[0];
-                        derotate_r4(comb(l0r, l1r, l2r) >> 16, comb(l0i, l1i, l2i) >> 16, r4.x, r4.y, p_re, p_im);
                     } else {
                         /* previous output = the column before my block; the phase word is its phase */
                         derotate_v2(comb(l0r, l1r, l2r) >> 16, comb(l0i, l1i, l2i) >> 16, r_re, r_im, p_re, p_im);
@@ -538,66 +489,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&t_empty[st]);  /* TMEM stage is free again */
-                    rp += 8;
                 }
 
                 /* ---- one channel x 8 consecutive outputs ---- */
                 const int nvalid = (p.K - kfirst > 8) ? 8 : (int)(p.K - kfirst);
-                if (live && nvalid > 0 && !(p.dbg_flags & 1)) {
+                if (live && nvalid > 0) {
                     /* EDGE = this block holds the submit's last output (or is cut short by it): also track y[K-1] */
                     auto block8 = [&](auto edge_tag) {
                         constexpr bool EDGE = decltype(edge_tag)::value;
                         int l_re = 0, l_im = 0;
                         float phi[8];
-                        /* phase 1: derotate, discriminate -> 8 angles, in two groups of four outputs whose arctangent
-                         * stages run side by side */
+                        /* phase 1: derotate, discriminate -> 8 angles, in two groups of four outputs = two packed pairs whose
+                         * arctangent stages run side by side (fm_math.cuh v3) */
 #pragma unroll
                         for (int g4 = 0; g4 < 2; g4++) {
                             int sre[4], sim[4];
-                            Atan2Stage as[4];
-                            float ex[4], ey[4];
 #pragma unroll
                             for (int v = 0; v < 4; v++) {
                                 const int u = 4 * g4 + v;
                                 int y_re, y_im;
-#if TC_DIAG & 4     /* diagnostics build: no derotator */
-                                y_re = x_re[u] >> 16; y_im = x_im[u] >> 16;
-#else
-                                if (ROT_TAB) {
-                                    const int2 r4 = rp[1 + u];
-                                    derotate_r4(x_re[u] >> 16, x_im[u] >> 16, r4.x, r4.y, y_re, y_im);
-                                } else {
-                                    derotate_v2(x_re[u] >> 16, x_im[u] >> 16, r_re, r_im, y_re, y_im);
-                                    rot_step_v2(r_re, r_im, i4_re, i4_im);
-                                }
-#endif
+                                derotate_v2(x_re[u] >> 16, x_im[u] >> 16, r_re, r_im, y_re, y_im);
+                                rot_step_v2(r_re, r_im, i4_re, i4_im);
                                 sre[v] = (int)((unsigned)y_re * (unsigned)p_re + (unsigned)y_im * (unsigned)p_im);    /* y * conj(prev) */
                                 sim[v] = (int)((unsigned)y_im * (unsigned)p_re - (unsigned)y_re * (unsigned)p_im);
                                 if (KEEP_IQ) { if (!EDGE || u < nvalid) iq_c[kfirst + u] = pack16(y_re, y_im); }
                                 p_re = y_re; p_im = y_im;
                                 if (EDGE) { if (u == nvalid - 1) { l_re = y_re; l_im = y_im; } }
-#if !(TC_DIAG & 2)
-                                atan2_stage1(sim[v], sre[v], as[v]);
-#endif
                             }
+                            Atan2Pair as[2];
+                            float ex[2][2], ey[2][2];
 #pragma unroll
-#if TC_DIAG & 2     /* diagnostics build: no arctangent */
-                            for (int v = 0; v < 4; v++) phi[4 * g4 + v] = (float)(sim[v] ^ sre[v]) * 1e-9f;
-#else
-                            for (int v = 0; v < 4; v++) atan2_stage2(as[v], atan_smem, atan_mul, ex[v], ey[v]);
+                            for (int q = 0; q < 2; q++) atan2p_stage1(sim[2 * q], sre[2 * q], sim[2 * q + 1], sre[2 * q + 1], as[q]);
 #pragma unroll
-                            for (int v = 0; v < 4; v++) phi[4 * g4 + v] = atan2_stage3<FMA>(sim[v], sre[v], as[v], ex[v], ey[v], z_thr);
-#endif
+                            for (int q = 0; q < 2; q++) atan2p_stage2(as[q], atan_smem, atan_mul, ex[q], ey[q]);
+#pragma unroll
+                            for (int q = 0; q < 2; q++)
+                                atan2p_stage3<FMA>(sim[2 * q], sre[2 * q], sim[2 * q + 1], sre[2 * q + 1], as[q], ex[q], ey[q], z_thr,
+                                                   phi[4 * g4 + 2 * q], phi[4 * g4 + 2 * q + 1]);
                         }
                         /* phase 2: angles -> PCM */
                         int pcm[8];
                         float margin = 1.0f;
 #pragma unroll
-#if TC_DIAG & 1     /* diagnostics build: no exact PCM scaling */
-                        for (int u = 0; u < 8; u++) pcm[u] = __float2int_rz(phi[u] * 5215.0f);
-#else
-                        for (int u = 0; u < 8; u++) { float a; pcm[u] = pcm_from_phi_v2(phi[u], a, margin); }
-#endif
+                        for (int q = 0; q < 4; q++) pcm_from_phi_pair(phi[2 * q], phi[2 * q + 1], margin, pcm[2 * q], pcm[2 * q + 1]);
                         if (margin < 0.0f) {    /* about 1 block in 4000: some output sits on a float rounding boundary -> FP64 */
 #pragma unroll
                             for (int u = 0; u < 8; u++) pcm[u] = pcm_from_phi_exact(__fmul_rn(phi[u], 16384.0f));
@@ -619,7 +553,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
                     else block8(std::true_type{});
                 }
             }
-            if (stamp) DBG(2, it >> 1, 4);
         }
     }
 
@@ -766,27 +699,6 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
     return pl;
 }
 
-/* After the derotator cycles are known: keep the longest period's phase table in shared memory if that leaves at
- * least 3 sample stages (or as many as there were).  lam_max = 0 (some channel has no tabulated cycle) disables it. */
-void tc_plan_reserve_rot(TcPlan &pl, unsigned lam_max, int smem_max)
-{
-    pl.rot_lt = 0;
-    if (!pl.ok || lam_max == 0) return;
-    int lt = 16;
-    while ((unsigned)lt < lam_max + 2 * TC_STEP + 1) lt *= 2;
-    if (lt > 256) return;
-    const size_t tab_bytes = (size_t)TC_CH * (lt + 1) * sizeof(int2);
-    const size_t static_smem = 2560 + 512;
-    const long long room = (long long)smem_max - (long long)static_smem - (long long)pl.a_group_bytes - 128 - (long long)tab_bytes - 2048LL * pl.atan_copies;
-    long long nb = room / (long long)pl.b_stage_bytes;
-    if (nb > NB_MAX) nb = NB_MAX;
-    if (nb < 3 && nb < pl.nb_stages) return;
-    if (nb < 2) return;
-    pl.nb_stages = (int)nb;
-    pl.rot_lt = lt;
-    pl.smem_bytes = pl.a_group_bytes + (size_t)pl.nb_stages * pl.b_stage_bytes + tab_bytes + 2048 * (size_t)pl.atan_copies + 128;
-}
-
 void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_im, std::vector<uint8_t> &img)
 {
     img.assign((size_t)pl.G * pl.a_group_bytes, 0);
@@ -835,20 +747,19 @@ size_t tc_max_ckpt_tiles(const TcPlan &, long long max_K, int)
     return (size_t)(max_K / TC_OUT + 2);
 }
 
-template <int MODE, bool KEEP_IQ, bool FMA, bool ROT_TAB>
+template <int MODE, bool KEEP_IQ, bool FMA>
 static cudaError_t launch_variant(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(tc_fir_fm_kernel<MODE, KEEP_IQ, FMA, ROT_TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_fir_fm_kernel<MODE, KEEP_IQ, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_fir_fm_kernel<MODE, KEEP_IQ, FMA, ROT_TAB><<<ctas, TC_THREADS, smem, st>>>(p);
+    tc_fir_fm_kernel<MODE, KEEP_IQ, FMA><<<ctas, TC_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 
 template <int MODE, bool KEEP_IQ>
-static cudaError_t launch_variant2(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st, bool fma, bool rot_tab)
+static cudaError_t launch_variant2(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st, bool fma)
 {
-    if (rot_tab) return fma ? launch_variant<MODE, KEEP_IQ, true, true>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, false, true>(p, ctas, smem, st);
-    return fma ? launch_variant<MODE, KEEP_IQ, true, false>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, false, false>(p, ctas, smem, st);
+    return fma ? launch_variant<MODE, KEEP_IQ, true>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, false>(p, ctas, smem, st);
 }
 
 cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st)
@@ -865,28 +776,17 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     p.C = pl.C; p.G = pl.G; p.Kp = pl.Kp; p.Q = pl.Q; p.R = pl.R;
     p.nb_stages = pl.nb_stages; p.prog_len = (int)pl.prog.size(); p.prog_split = pl.prog_split;
     p.prog_regular = pl.prog_regular ? 1 : 0;
-    p.inv_nslab = 1.0f / (float)(pl.Kp / 16);
     p.a_group_bytes = (uint32_t)pl.a_group_bytes; p.b_stage_bytes = (uint32_t)pl.b_stage_bytes;
     p.atan = b.atan;
-    p.dbg = b.dbg;
-    p.dbg_flags = b.dbg_flags;
-    p.tune = b.tune;
-    p.sleep_epi = b.sleep_ns[0]; p.sleep_xf = b.sleep_ns[1]; p.sleep_mma = b.sleep_ns[2];
     memcpy(p.prog, pl.prog.data(), pl.prog.size() * sizeof(TcMma));
     /* persistent grid: one CTA per (tile range, channel group), at most one per SM */
     const unsigned ctas = (unsigned)b.geom.chunks * (unsigned)pl.G;
     const bool iq = b.iq_out != nullptr, fma = b.atan.use_fma != 0;
-    /* the phase table needs the steady state (ckpt == nullptr) and room in shared memory (tc_plan_reserve_rot) */
-    /* Measured on B200 (64 ch x 127 taps / D = 100): 0.110 ms with the table, 0.105 ms with the recurrence -- the
-     * 9 LDS.64 per block cost more (LSU queue, shared-memory bandwidth next to the tensor core's operand reads and
-     * the transform's stores) than the 10 integer instructions per output they replace.  Opt-in: GPUCHAN_TC_TUNE |= 8. */
-    const bool rot_tab = b.ckpt == nullptr && pl.rot_lt > 0 && (b.tune & 8);
-    p.rot_lt = rot_tab ? pl.rot_lt : 0;
     p.atan_copies = pl.atan_copies;
     const size_t sm = pl.smem_bytes;
     if (pl.mode == TC_MODE_RADIX)
-        return iq ? launch_variant2<TC_MODE_RADIX, true>(p, ctas, sm, st, fma, rot_tab) : launch_variant2<TC_MODE_RADIX, false>(p, ctas, sm, st, fma, rot_tab);
-    return iq ? launch_variant2<TC_MODE_SUM, true>(p, ctas, sm, st, fma, rot_tab) : launch_variant2<TC_MODE_SUM, false>(p, ctas, sm, st, fma, rot_tab);
+        return iq ? launch_variant2<TC_MODE_RADIX, true>(p, ctas, sm, st, fma) : launch_variant2<TC_MODE_RADIX, false>(p, ctas, sm, st, fma);
+    return iq ? launch_variant2<TC_MODE_SUM, true>(p, ctas, sm, st, fma) : launch_variant2<TC_MODE_SUM, false>(p, ctas, sm, st, fma);
 }
 
 } // namespace tslb200

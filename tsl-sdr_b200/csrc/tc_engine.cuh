@@ -48,7 +48,6 @@ struct TcPlan {
     size_t b_stage_bytes = 0;           /* bytes of one sample tile (both planes) */
     size_t smem_bytes = 0;
     int atan_copies = 1;                /* interleaved copies of the arctangent table in shared memory (16 or 1) */
-    int rot_lt = 0;                     /* entries per channel of the in-kernel derotator phase table (0 = none) */
     std::vector<TcMma> prog;            /* the MMAs of one tile: [0, prog_split) issued by MMA warp 0, the rest by warp 1 */
     bool prog_regular = false;          /* (accumulator, descriptor) alternate even/odd within each warp's part: fast issue path */
     int prog_split = 0;                 /* the two warps own disjoint accumulators, so their order does not matter */
@@ -58,7 +57,6 @@ struct TcPlan {
 };
 
 TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_im, int smem_max);
-void tc_plan_reserve_rot(TcPlan &pl, unsigned lam_max, int smem_max);
 /* tap image for all groups: [G][a_chunks][2 slabs][128 rows][16] bytes */
 void tc_build_tap_image(const TcPlan &pl, const int16_t *c_re, const int16_t *c_im, std::vector<uint8_t> &img);
 
@@ -91,10 +89,6 @@ struct TcBatch {
     unsigned long long K;
     TcGeom geom;
     AtanParams atan;
-    long long *dbg = nullptr;
-    int dbg_flags = 0;
-    int tune = 0;
-    uint32_t sleep_ns[3] = { 200, 1000, 100 };   /* poll intervals: epilogue, transform, MMA issuers */
 };
 
 cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st);
