@@ -6,7 +6,9 @@ Default workload = the shape BASELINE.json's north_star quotes its target on: 25
 100, 2.4 MS/s, per B200 (--config c2|c3|c4|c5 select BASELINE.json's other shapes; c4 is the strong-scaling sweep).
   value : channel-samples/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e   : same metric through the C ABI with HOST buffers: pinned H2D of every batch + D2H of all PCM inside the
-          timed region.  N > 1: every GPU pulls the batch over its OWN PCIe link from one shared pinned host segment.
+          timed region.  N > 1: the batch crosses PCIe ONCE (pinned host -> ingest GPU), rides the relay chain, and every
+          GPU returns its channels' PCM over its own PCIe link (--e2e-fanout host: every GPU instead copies the batch
+          itself from one shared pinned host segment; measured NUMA-bound on the 8-GPU boxes).
   N > 1 : channels shard across ranks; the only data-path exchange is the fan-out of the IQ batch from the ingest GPU
           (rank 0), inside the timed region: a pipelined relay chain over NVLink driven by the copy engines
           (include/tslb200_gpurelay.h), or torch.distributed.broadcast (NCCL) with --fanout nccl.
@@ -247,6 +249,29 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """Run this rank (and therefore first-touch its pinned host buffers) on the NUMA node its GPU hangs off, as a
+    multi-socket receiver would place its per-GPU staging: without it the DMA of seven of eight GPUs crosses the socket
+    interconnect.  Returns the node or None when the platform does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 class SharedPinned:
     """One copy of the IQ batches in host memory for all ranks of the box (the single ingest buffer of a receiver
     process): a /dev/shm segment every rank maps and page-locks, so each GPU DMAs it over its own PCIe link."""
@@ -289,6 +314,7 @@ def main():
     ap.add_argument("--submits", type=int, default=8, help="submits per step (keeps the timed region well above 50 ms)")
     ap.add_argument("--engine", type=int, default=0)
     ap.add_argument("--fanout", default="relay", choices=["relay", "nccl"], help="N > 1: how the IQ batch reaches the other GPUs")
+    ap.add_argument("--e2e-fanout", default="relay", choices=["relay", "host"], help="N > 1: how the host batch reaches the GPUs in the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -310,6 +336,7 @@ def main():
         raise SystemExit("bench.py needs a GPU: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -379,10 +406,17 @@ def main():
 
     # host buffers of the end-to-end leg, allocated up front so that the two timed legs run back to back (the clock
     # sampler spans both; an idle gap between them would show up as low clocks)
-    host_in = SharedPinned(torch, dist, rank, NB * 4 * n, os.environ.get("MASTER_PORT", str(os.getpid())))
-    if rank == 0:
-        for b in range(NB):
-            host_in.arr[b * 2 * n:(b + 1) * 2 * n] = batches[b].cpu().numpy()
+    e2e_relay = relay is not None and args.e2e_fanout == "relay"
+    host_in = pin_in = None
+    if e2e_relay:
+        if rank == 0:                                   # the one host copy of the stream lives with the ingest rank
+            pin_in = [batches[b].cpu().pin_memory() for b in range(NB)]
+        h2d_stream = torch.cuda.Stream(device=dev)
+    else:
+        host_in = SharedPinned(torch, dist, rank, NB * 4 * n, os.environ.get("MASTER_PORT", str(os.getpid())))
+        if rank == 0:
+            for b in range(NB):
+                host_in.arr[b * 2 * n:(b + 1) * 2 * n] = batches[b].cpu().numpy()
     pin_out = torch.empty((c_gpu, n // D + 16), dtype=torch.int16).pin_memory()
     barrier()
 
@@ -433,7 +467,21 @@ def main():
     def e2e_submit():
         i = eseq[0]
         eseq[0] += 1
-        bank.submit_ptr(host_in.ptr + (i % NB) * 4 * n, n)              # pinned H2D inside the C ABI call, this GPU's own link
+        if not e2e_relay:
+            bank.submit_ptr(host_in.ptr + (i % NB) * 4 * n, n)          # pinned H2D inside the C ABI call, this GPU's own link
+            return
+        q = seq[0]                                                      # the relay's batch numbering continues
+        seq[0] += 1
+        slot = batches[q % NBUF]
+        producer = 0
+        if rank == 0:                                                   # host -> ingest GPU: the only PCIe crossing of the input
+            relay.acquire(q, h2d_stream.cuda_stream)
+            with torch.cuda.stream(h2d_stream):
+                slot.copy_(pin_in[i % NB], non_blocking=True)
+            producer = h2d_stream.cuda_stream
+        rs = relay.advance(q, 4 * n, producer_stream=producer)
+        bank.submit_device(slot.data_ptr(), n, rs)
+        relay.consumed(q, bank)
 
     def e2e_collect():
         return bank.collect_into(pin_out.data_ptr(), pin_out.shape[1])  # D2H of every channel's PCM, blocking
@@ -478,12 +526,14 @@ def main():
             "config": config_dict(args, cfg, world),
             "engine": engine,
             "fanout": (args.fanout if world > 1 else None),
+            "host_numa_node_rank0": numa_node,
             "iq_msps": value * D / cfg["c_total"] / 1e6,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n * S * world,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n * S * (1 if (world == 1 or e2e_relay) else world),
                     "d2h_bytes_per_step": 2 * c_gpu * k_per_submit * S * world, "pcm_checksum": checksum,
-                    "note": "every GPU copies the batch over its own PCIe link from one shared pinned host segment" if world > 1 else
+                    "note": ("pinned host batch -> ingest GPU (one PCIe crossing) -> NVLink relay chain -> every GPU's PCM back over its own PCIe link"
+                             if e2e_relay else "every GPU copies the batch over its own PCIe link from one shared pinned host segment") if world > 1 else
                             "pinned host batch -> gpuchan_submit -> gpuchan_collect into pinned host PCM"},
             "roofline": {"bound": "hbm", "kernel": "tc_fir_fm_kernel (fused mix+FIR+decimate+derotate+FM)" if engine == "tc" else "fir_fm_imad_kernel",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -513,7 +563,8 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(exc)}
         print(json.dumps(line))
     bank.close()
-    host_in.close()
+    if host_in is not None:
+        host_in.close()
     if relay is not None:
         relay.close()
     if dist is not None:

@@ -202,6 +202,11 @@ int gpuchan_tc_plan_query(const gpuchan_cfg *cfg, uint32_t smem_max_bytes, uint3
  * path, out[3] = offenders recorded, out[4..7] = the first offender's operands and results. */
 int gpuchan_math_selftest(uint32_t what, uint64_t seed_or_first, uint64_t count, uint32_t use_fma, uint64_t out[8]);
 
+/* Unit hook for tests: the fused kernel's discriminator arithmetic (fm_math.cuh v3, packed pairs) on caller-provided int32
+ * operand pairs: phi[i] = fast_atan2f((float)s_im[i], (float)s_re[i]) and pcm[i] = (int16)(float)((double)phi / M_PI * 16384)
+ * (multifm/fm_demod.c:66-72), for comparison with fixtures recorded from the reference objects. */
+int gpuchan_math_eval(const int32_t *s_im, const int32_t *s_re, size_t n, uint32_t use_fma, float *phi, int16_t *pcm);
+
 #ifdef __cplusplus
 }
 #endif

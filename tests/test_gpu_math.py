@@ -34,3 +34,31 @@ def test_pcm_scaling_exhaustive(pkg, first):
     out = _run(pkg, 1, first, count, 1)
     assert out[1] == 0, f"{out[1]} PCM values differ; first: phi bits {out[4]:#x} ref {np.int32(np.uint32(out[5]))} got {np.int32(np.uint32(out[6]))}"
     assert 0 < out[2] < count // 100000
+
+
+@pytest.mark.parametrize("fma", [1, 0])
+def test_kernel_arithmetic_against_the_reference_fixture_and_the_oracle(pkg, oracle, fma):
+    """The fused kernel's packed-pair arithmetic against what the REFERENCE objects computed (tests/golden/atan2.npz,
+    recorded from multifm/fast_atan2f.c in both contraction variants) and against the oracle's discriminator
+    (multifm/fm_demod.c:66-72) -- not only against our own device transcription."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "atan2.npz"))
+    rng = np.random.default_rng(7)
+    extra_im = rng.integers(-2**31, 2**31, 200000, dtype=np.int64)
+    extra_re = rng.integers(-2**31, 2**31, 200000, dtype=np.int64) >> rng.integers(0, 31, 200000)
+    s_im = np.concatenate([z["s_im"], extra_im]).astype(np.int32)
+    s_re = np.concatenate([z["s_re"], extra_re]).astype(np.int32)
+    n = len(s_im)
+    phi = np.zeros(n, np.float32)
+    pcm = np.zeros(n, np.int16)
+    rc = pkg._lib.lib().gpuchan_math_eval(s_im.ctypes.data, s_re.ctypes.data, n, fma, phi.ctypes.data, pcm.ctypes.data)
+    assert rc == 0, pkg._lib.lib().gpuchan_last_error()
+    want = z["phi" if fma else "phi_nofma"]
+    got = phi[:len(want)]
+    same = (got.view(np.uint32) == want.view(np.uint32)) | ((got == 0) & (want == 0))
+    assert same.all(), f"{(~same).sum()} of {len(want)} angles differ from the reference fixture"
+    exp_phi = np.array([oracle.L.orc_fast_atan2f(np.float32(a), np.float32(b), fma) for a, b in zip(s_im[:20000], s_re[:20000])], np.float32)
+    g = phi[:20000]
+    assert ((g.view(np.uint32) == exp_phi.view(np.uint32)) | ((g == 0) & (exp_phi == 0))).all()
+    exp_pcm = (phi.astype(np.float64) / np.pi * 16384.0).astype(np.float32).astype(np.int32).astype(np.int16)   # fm_demod.c:71-72
+    assert np.array_equal(pcm, exp_pcm)

@@ -82,6 +82,7 @@ def _declare(L: C.CDLL) -> None:
     L.gpuchan_tc_plan_query.argtypes = [C.POINTER(GpuChanCfg), C.c_uint32, vp, vp, sz, vp, sz]
     L.gpuchan_math_selftest.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, vp]
     L.gpuchan_discard.argtypes = [vp]
+    L.gpuchan_math_eval.argtypes = [vp, vp, sz, C.c_uint32, vp, vp]
     L.gpuchan_tc_model.argtypes = [vp, vp]
     L.gpuchan_collect_begin.argtypes = [vp, vp, sz]
     L.gpuchan_collect_end.argtypes = [vp, C.POINTER(sz)]
@@ -148,7 +149,7 @@ EXPORTS = ["gpuchan_prepare_taps", "gpuchan_derot_increment", "gpuchan_db_to_gai
            "gpuchan_destroy", "gpuchan_submit", "gpuchan_submit_device", "gpuchan_submit_bytes", "gpuchan_sync", "gpuchan_pending",
            "gpuchan_collect", "gpuchan_collect_iq", "gpuchan_device_pcm", "gpuchan_get_taps",
            "gpuchan_get_rot_state", "gpuchan_engine", "gpuchan_kernel_launches", "gpuchan_last_error", "gpuchan_timing_enable", "gpuchan_in_flight", "gpuchan_discard", "gpuchan_host_alloc", "gpuchan_host_free", "gpuchan_tc_selftest", "gpuchan_math_selftest", "gpuchan_tc_plan_query", "gpuchan_stream_wait",
-           "gpuchan_timing_read", "gpuchan_tc_model", "gpuchan_collect_begin", "gpuchan_collect_end",
+           "gpuchan_timing_read", "gpuchan_tc_model", "gpuchan_math_eval", "gpuchan_collect_begin", "gpuchan_collect_end",
            "gpuchan_multi_create", "gpuchan_multi_destroy", "gpuchan_multi_submit", "gpuchan_multi_pending", "gpuchan_multi_collect",
            "gpuchan_multi_discard", "gpuchan_multi_sync", "gpuchan_multi_devices", "gpuchan_multi_bank",
            "gpurelay_flags_bytes", "gpurelay_create", "gpurelay_destroy", "gpurelay_slot", "gpurelay_export", "gpurelay_connect_ipc",

@@ -535,6 +535,23 @@ extern "C" int gpuchan_math_selftest(uint32_t what, uint64_t seed_or_first, uint
     return GPUCHAN_OK;
 }
 
+namespace tslb200 {
+cudaError_t run_math_eval(const int *h_im, const int *h_re, size_t n, bool use_fma, const float2 *h_tab, float z_small_thr,
+                          float *h_phi, short *h_pcm);
+}
+
+extern "C" int gpuchan_math_eval(const int32_t *s_im, const int32_t *s_re, size_t n, uint32_t use_fma, float *phi, int16_t *pcm)
+{
+    if (!s_im || !s_re || !phi || !pcm || !n) return set_err(GPUCHAN_E_BADARGS, "bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(GPUCHAN_E_NODEVICE, "no CUDA device: this library has no CPU fallback");
+    float2 tab[256];
+    host_atan_table(tab);
+    CUDA_TRY(tslb200::run_math_eval(s_im, s_re, n, use_fma != 0, tab, host_z_small_thr(), phi, pcm));
+    return GPUCHAN_OK;
+}
+
 /* Host-only view of the tensor-core plan (no device needed): lets the CPU test-suite check the int8 limb
  * decomposition, the tap image and the per-tile MMA program by emulating them against the direct integer FIR. */
 extern "C" int gpuchan_tc_plan_query(const gpuchan_cfg *cfg, uint32_t smem_max_bytes, uint32_t info[16],

@@ -136,9 +136,59 @@ __global__ void pcm_selftest_kernel(uint32_t first, uint64_t count, unsigned lon
     atomicAdd(&out[2], exact);
 }
 
+/* the fused kernel's arithmetic (v3 pairs) on caller-provided operands: element i rides in the half i & 1 of its pair */
+template <bool FMA>
+__global__ void eval_kernel(const int *__restrict__ s_im, const int *__restrict__ s_re, size_t n, const float2 *tab_g, float z_thr,
+                            float *__restrict__ phi_out, short *__restrict__ pcm_out)
+{
+    __shared__ float2 tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = tab_g[i];
+    __syncthreads();
+    const uint32_t tab_biased = (uint32_t)__cvta_generic_to_shared(tab) - 0x4B000000u * 8u;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; 2 * p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const size_t i0 = 2 * p, i1 = (2 * p + 1 < n) ? 2 * p + 1 : 2 * p;
+        Atan2Pair a;
+        float ex[2], ey[2], phi[2], margin = 1.0f;
+        int pcm[2];
+        atan2p_stage1(s_im[i0], s_re[i0], s_im[i1], s_re[i1], a);
+        atan2p_stage2(a, tab_biased, 8u, ex, ey);
+        atan2p_stage3<FMA>(s_im[i0], s_re[i0], s_im[i1], s_re[i1], a, ex, ey, z_thr, phi[0], phi[1]);
+        pcm_from_phi_pair(phi[0], phi[1], margin, pcm[0], pcm[1]);
+        if (margin < 0.0f) { pcm[0] = pcm_from_phi_exact(__fmul_rn(phi[0], 16384.0f)); pcm[1] = pcm_from_phi_exact(__fmul_rn(phi[1], 16384.0f)); }
+        phi_out[i0] = phi[0]; pcm_out[i0] = (short)pcm[0];
+        if (i1 != i0) { phi_out[i1] = phi[1]; pcm_out[i1] = (short)pcm[1]; }
+    }
+}
+
 } // namespace
 
 namespace tslb200 {
+
+cudaError_t run_math_eval(const int *h_im, const int *h_re, size_t n, bool use_fma, const float2 *h_tab, float z_small_thr,
+                          float *h_phi, short *h_pcm)
+{
+    int *d_im = nullptr, *d_re = nullptr;
+    float *d_phi = nullptr;
+    short *d_pcm = nullptr;
+    float2 *d_tab = nullptr;
+    cudaError_t e = cudaMalloc(&d_im, n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_re, n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_phi, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_pcm, n * sizeof(short));
+    if (e == cudaSuccess) e = cudaMalloc(&d_tab, 256 * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpy(d_im, h_im, n * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_re, h_re, n * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_tab, h_tab, 256 * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        if (use_fma) eval_kernel<true><<<64, 256>>>(d_im, d_re, n, d_tab, z_small_thr, d_phi, d_pcm);
+        else eval_kernel<false><<<64, 256>>>(d_im, d_re, n, d_tab, z_small_thr, d_phi, d_pcm);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(h_phi, d_phi, n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(h_pcm, d_pcm, n * sizeof(short), cudaMemcpyDeviceToHost);
+    cudaFree(d_im); cudaFree(d_re); cudaFree(d_phi); cudaFree(d_pcm); cudaFree(d_tab);
+    return e;
+}
 
 /* what = 0: `count` pseudo-random operand pairs through the arctangent and the PCM scaling;
  * what = 1: float bit patterns [seed_or_first, seed_or_first + count) through the PCM scaling.
