@@ -48,7 +48,7 @@ def test_both_arms_describe_the_same_config():
     import bench
     for name in bench.CONFIGS:
         for n_gpus in (1, 2, 8):
-            args = argparse.Namespace(config=name, batch_log2=25, submits=8)
+            args = argparse.Namespace(config=name, batch_log2=25, submits=16)
             cfg = bench.shape(args, n_gpus)
             d = bench.config_dict(args, cfg, n_gpus)
             assert set(d) == {"workload", "channels", "channels_per_gpu", "taps", "decimation", "fs", "batch_complex_samples",

@@ -12,7 +12,8 @@
  *                     registers, 16-word batch sampled 32 bits per ballot, BCH(31,21) correction, address / alpha /
  *                     numeric assembly (pager/pager_pocsag.c:82-543, pager/bch_code.c:307-398).  Messages are queued per
  *                     channel for the host callbacks.
- *   flex_kernel       one thread per channel over the resampled 16000 Hz stream: optional DC blocker, Sync 1
+ *   flex_kernel       one WARP per channel over the resampled 16000 Hz stream (30 samples of bit-sync search per step,
+ *                     lane 0 through the rest of a frame): optional DC blocker, Sync 1
  *                     (10-phase bit-sync search, A / B / inverted A, FIW), slicer training, Sync 2, 4 codings
  *                     (1600/2, 3200/2, 3200/4, 6400/4), block de-interleave into up to 4 phases, BCH + checksum,
  *                     BIW / address / vector walk, alphanumeric / numeric / tone / SIV assembly
@@ -342,6 +343,7 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pocsag_kernel(PocsagState *__re
     /* ---- pass 1: DC blocker (filter/dc_blocker.h:79-88) and slicer ---- */
     {
         int dc_x = S.dc_x, dc_y = S.dc_y, dc_acc = S.dc_acc;
+        __syncwarp();                               /* every lane has read the state before lane 0 writes it back below */
         for (unsigned g0 = 0; g0 < n; g0 += 32) {
             const unsigned idx = g0 + lane;
             int v = idx < n ? (int)x[idx] : 0;
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pocsag_kernel(PocsagState *__re
     if (S.state == ST_SYNCHRONIZED) { if (lane == 0) S.state = ST_BATCH; __syncwarp(); }
     while (i < n) {
         const int state = S.state;
+        __syncwarp();                               /* scalars are read by every lane before lane 0 updates them further down */
         if (state == ST_SEARCH) {
             const unsigned cnt = min(32u, n - i);
             const unsigned word = __funnelshift_r(bits[i >> 5], bits[(i >> 5) + 1], i & 31);
@@ -428,6 +431,7 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pocsag_kernel(PocsagState *__re
             const unsigned spb = S.sample_skip;
             const unsigned skip = batch ? S.b_skip : S.s_skip;
             const unsigned have = batch ? S.b_word_bit : S.s_bits;
+            __syncwarp();
             const unsigned long long first = (unsigned long long)i + until_sampling(spb, skip) - 1;
             const unsigned long long pos = first + (unsigned long long)lane * spb;
             const bool valid = (unsigned)lane < 32 - have && pos < n;
@@ -922,54 +926,129 @@ __device__ void fx_block_update(FlexState &f, const MsgSink &sink, int c, int sa
     }
 }
 
-/* pager_flex_on_pcm (:1401-1455), one thread per channel, state worked on in place (L1/L2 resident) */
-__global__ void flex_kernel(FlexState *__restrict__ states, int nr_channels, short *__restrict__ pcm, long long pitch, unsigned n,
-                            MsgSink sink, int use_dc, int dc_p)
+/* pager_flex_on_pcm (:1401-1455), one WARP per channel.
+ *   pass 1  the optional DC blocker over the whole feed (every lane computes the identical recurrence);
+ *   pass 2  the state machine.  Where a receiver spends nearly all of its time -- searching for bit sync, Sync 1 state
+ *           SEARCH_BS1 (:296-345): every sample shifts into one of 10 phase registers, round robin, and is compared with
+ *           0xaaaaaaaa -- the warp takes 30 samples per step: lane j handles sample j, in three sub-passes of ten lanes
+ *           (ten distinct registers each); on a hit the lanes behind it in the same sub-pass put their register back and
+ *           lane 0 carries on sample by sample with the reference's logic (fx_sync_update and friends, unchanged) until
+ *           the machine is back in SEARCH_BS1.  Those sequential stretches (one frame: 1.9 s of signal) see every
+ *           (skip + 1)-th sample only. */
+constexpr int FW_WARPS = 4;
+
+__device__ void flex_step_sequential(FlexState &f, const MsgSink &sink, int c, int sample)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nr_channels) return;
+    if (f.skip_count != 0) { f.skip_count--; return; }
+    f.skip_count = f.skip;
+    switch (f.state) {
+    case FX_SYNC_1:
+        fx_sync_update(f, sample);
+        if (f.sync_state == FS_SYNCED) {
+            /* _pager_flex_handle_fiw :1312-1345 */
+            uint32_t fiw = f.fiw & 0x7fffffffu;
+            bool ok = bch_decode(fiw) == 0;
+            if (ok) {
+                f.cycle_id = (fiw >> 4) & 0xf;
+                f.frame_id = (fiw >> 8) & 0x7f;
+                ok = fx_cksum(fiw) == 0xf;
+            }
+            if (ok) {
+                f.state = FX_SYNC_2;
+                f.skip = c_flex_codings[f.coding].sample_skip;
+                f.skip_count = f.skip + c_flex_codings[f.coding].sample_fudge;
+            } else {
+                fx_reset(f);
+            }
+        }
+        break;
+    case FX_SYNC_2:
+        fx_sync2_update(f, sample);
+        if (f.s2_state == F2_SYNCED) f.state = FX_BLOCK;
+        break;
+    default:
+        fx_block_update(f, sink, c, sample);
+        break;
+    }
+}
+
+__device__ __forceinline__ bool flex_searching(const FlexState &f)
+{
+    return f.state == FX_SYNC_1 && f.sync_state == FS_SEARCH_BS1 && f.skip == 0 && f.skip_count == 0;
+}
+
+__global__ void __launch_bounds__(32 * FW_WARPS) flex_kernel(FlexState *states, int nr_channels, short *pcm,
+                                                             long long pitch, unsigned n, MsgSink sink, int use_dc, int dc_p)
+{
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * FW_WARPS + (threadIdx.x >> 5);
+    if (c >= nr_channels) return;                   /* whole warps leave */
     FlexState &f = states[c];
     short *x = pcm + (size_t)c * pitch;
-    for (unsigned i = 0; i < n; i++) {
-        int sample = x[i];
-        if (use_dc) {                       /* filter/dc_blocker.h:79-88 */
-            f.dc_acc -= f.dc_x;
-            f.dc_x = sample << 14;
-            f.dc_acc += f.dc_x - dc_p * f.dc_y;
-            f.dc_y = f.dc_acc >> 14;
-            sample = (int)(short)f.dc_y;
-            x[i] = (short)sample;
-        }
-        if (f.skip_count != 0) { f.skip_count--; continue; }
-        f.skip_count = f.skip;
-        switch (f.state) {
-        case FX_SYNC_1:
-            fx_sync_update(f, sample);
-            if (f.sync_state == FS_SYNCED) {
-                /* _pager_flex_handle_fiw :1312-1345 */
-                uint32_t fiw = f.fiw & 0x7fffffffu;
-                bool ok = bch_decode(fiw) == 0;
-                if (ok) {
-                    f.cycle_id = (fiw >> 4) & 0xf;
-                    f.frame_id = (fiw >> 8) & 0x7f;
-                    ok = fx_cksum(fiw) == 0xf;
-                }
-                if (ok) {
-                    f.state = FX_SYNC_2;
-                    f.skip = c_flex_codings[f.coding].sample_skip;
-                    f.skip_count = f.skip + c_flex_codings[f.coding].sample_fudge;
-                } else {
-                    fx_reset(f);
-                }
+
+    if (use_dc) {                                   /* filter/dc_blocker.h:79-88 */
+        int dc_x = f.dc_x, dc_y = f.dc_y, dc_acc = f.dc_acc;
+        __syncwarp();
+        for (unsigned g0 = 0; g0 < n; g0 += 32) {
+            const unsigned idx = g0 + lane, cnt = min(32u, n - g0);
+            const int v = idx < n ? (int)x[idx] : 0;
+            int mine = v;
+            for (unsigned t = 0; t < cnt; t++) {
+                const int sample = __shfl_sync(0xffffffffu, v, t);
+                dc_acc -= dc_x;
+                dc_x = sample << 14;
+                dc_acc += dc_x - dc_p * dc_y;
+                dc_y = dc_acc >> 14;
+                if ((unsigned)lane == t) mine = (int)(short)dc_y;
             }
-            break;
-        case FX_SYNC_2:
-            fx_sync2_update(f, sample);
-            if (f.s2_state == F2_SYNCED) f.state = FX_BLOCK;
-            break;
-        default:
-            fx_block_update(f, sink, c, sample);
-            break;
+            if (idx < n) x[idx] = (short)mine;
+        }
+        __syncwarp();
+        if (lane == 0) { f.dc_x = dc_x; f.dc_y = dc_y; f.dc_acc = dc_acc; }
+        __syncwarp();
+    }
+
+    unsigned i = 0;
+    while (i < n) {
+        if (flex_searching(f)) {
+            /* ---- 30 samples of bit-sync search ---- */
+            const unsigned cnt = min(30u, n - i);
+            const unsigned sc0 = f.sample_counter;
+            const bool have = (unsigned)lane < cnt;
+            const uint32_t sym = (have && x[i + lane] >= 0) ? 1u : 0u;
+            const unsigned ph = (sc0 + 1 + (unsigned)lane) % 10;
+            int hit_at = -1;
+            __syncwarp();
+            for (int sub = 0; sub < 3 && hit_at < 0; sub++) {
+                const bool mine = have && lane / 10 == sub;
+                uint32_t old = 0, w = 0;
+                if (mine) { old = f.sync_words[ph]; w = (old << 1) | sym; f.sync_words[ph] = w; }
+                const unsigned hits = __ballot_sync(0xffffffffu, mine && w == 0xaaaaaaaau);
+                if (hits) {
+                    hit_at = __ffs(hits) - 1;
+                    if (mine && lane > hit_at) f.sync_words[ph] = old;      /* samples behind the hit have not happened yet */
+                }
+                __syncwarp();
+            }
+            if (hit_at >= 0) {
+                if (lane == 0) { f.sample_counter = (sc0 + 1 + (unsigned)hit_at) % 10; f.bit_counter = 1; f.sync_state = FS_BS1; }
+                i += (unsigned)hit_at + 1;
+            } else {
+                if (lane == 0) f.sample_counter = (sc0 + cnt) % 10;
+                i += cnt;
+            }
+            __syncwarp();
+        } else {
+            /* ---- lane 0 walks the reference's state machine until it is searching again ---- */
+            unsigned j = i;
+            if (lane == 0) {
+                do {
+                    flex_step_sequential(f, sink, c, (int)x[j]);
+                    j++;
+                } while (j < n && !flex_searching(f));
+            }
+            i = __shfl_sync(0xffffffffu, j, 0);
+            __syncwarp();
         }
     }
 }
@@ -1210,8 +1289,8 @@ static int pager_run(gpupager *h, const short *d_pcm, size_t pitch, size_t n, cu
     if (nr_dec) {
         MsgSink sink{ h->d_map, h->d_msgs, h->d_count, h->d_dropped, h->msg_cap };
         if (h->decoder == GPUPAGER_DECODER_FLEX)
-            flex_kernel<<<(C + 31) / 32, 32, 0, st>>>(h->d_fstates, C, const_cast<short *>(dec_in), dec_pitch, nr_dec, sink,
-                                                      (h->flags & GPUPAGER_F_DC_BLOCK) ? 1 : 0, h->dc_p);
+            flex_kernel<<<(C + FW_WARPS - 1) / FW_WARPS, 32 * FW_WARPS, 0, st>>>(h->d_fstates, C, const_cast<short *>(dec_in), dec_pitch, nr_dec, sink,
+                                                                                  (h->flags & GPUPAGER_F_DC_BLOCK) ? 1 : 0, h->dc_p);
         else
             pocsag_kernel<<<(C + PW_WARPS - 1) / PW_WARPS, 32 * PW_WARPS, 0, st>>>(h->d_states, h->d_text, C, const_cast<short *>(dec_in), dec_pitch,
                                                                                     nr_dec, h->d_bits, h->bits_pitch, sink,
