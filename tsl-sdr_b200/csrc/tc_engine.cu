@@ -44,7 +44,10 @@ namespace tslb200 {
 namespace {
 
 constexpr int EPI_WARPS = 16;
-constexpr int XF_WARPS = 8;             /* transform warps: raw cs16 -> byte planes in smem */
+#ifndef TC_XF_WARPS
+#define TC_XF_WARPS 8
+#endif
+constexpr int XF_WARPS = TC_XF_WARPS;   /* transform warps: raw cs16 -> byte planes in smem */
 constexpr int XF_THREADS = 32 * XF_WARPS;
 /* The transform warps form one group per sample stage (warp w -> group w % NB); a group fills its stage on its own,
  * so NB tiles' loads are in flight at any time.  One group per stage also keeps every barrier wait at most one
