@@ -1,18 +1,16 @@
-/* Drop-in for multifm/fm_demod.h:22-34: same three entry points, same argument meaning, same results bit for bit
- * (multifm/fm_demod.c:36-85, multifm/fast_atan2f.c:101-174) -- computed by the B200 library (gpufm_* in
- * tslb200_gpuchan.h).  There is no CPU path: _init fails when no sm_100 device is present. */
-#pragma once
-
+/* The FM discriminator object of multifm/fm_demod.h:22-34 on the B200 library: same three entry points, same argument
+ * meaning and results (multifm/fm_demod.c:36-85, multifm/fast_atan2f.c:101-174 bit for bit), backed by gpufm_* in
+ * tslb200_gpuchan.h.  There is no CPU path: _init fails when no sm_100 device is present. */
+#ifndef TSLB200_COMPAT_FM_DEMOD_H
+#define TSLB200_COMPAT_FM_DEMOD_H
 #include <tsl/result.h>
 
 struct demod_base;
 
-/* multifm/fm_demod.h:22 */
-aresult_t multifm_fm_demod_init(struct demod_base **pdemod);
-
-/* multifm/fm_demod.h:28: nr_in_samples complex int16 pairs in, one int16 PCM sample each out */
-aresult_t multifm_fm_demod_process(struct demod_base *demod, int16_t *in_samples, size_t nr_in_samples,
-        int16_t *out_samples, size_t *pnr_out_samples, size_t *pnr_out_bytes);
-
-/* multifm/fm_demod.h:34 */
-aresult_t multifm_fm_demod_cleanup(struct demod_base **pdemod);
+/* fm_demod.h:22 -- new discriminator; *handle receives it */
+aresult_t multifm_fm_demod_init(struct demod_base **handle);
+/* fm_demod.h:28 -- nr_iq complex int16 pairs in, one int16 PCM sample each out; *nr_pcm and *nr_pcm_bytes report what was written */
+aresult_t multifm_fm_demod_process(struct demod_base *handle, int16_t *iq, size_t nr_iq, int16_t *pcm, size_t *nr_pcm, size_t *nr_pcm_bytes);
+/* fm_demod.h:34 -- release; *handle becomes NULL */
+aresult_t multifm_fm_demod_cleanup(struct demod_base **handle);
+#endif
