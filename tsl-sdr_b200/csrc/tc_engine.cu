@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
     constexpr int NT = 512 / (ACCS * TC_ACC_STRIDE);            /* TMEM stages: 3 (SUM) or 2 (RADIX) */
     constexpr uint32_t STAGE_COLS = ACCS * TC_ACC_STRIDE;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t b_full[NB_MAX], b_empty[NB_MAX], t_full[NT_MAX], t_empty[NT_MAX];
+    __shared__ __align__(8) uint64_t b_full[NB_MAX], b_empty[NB_MAX], t_full[NT_MAX], t_empty[NT_MAX], a_full;
     __shared__ uint32_t tmem_base_s;
     __shared__ TcMma prog_s[TC_PROG_MAX];
 
@@ -171,17 +171,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
     if (tid < NB) prefetch_tile(tile0 + tid, tid == 0);
 
     /* ---- one-time setup ---- */
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.tap_img + (size_t)g * p.a_group_bytes);
-        uint4 *dst = reinterpret_cast<uint4 *>(sA);
-        for (uint32_t i = tid; i < p.a_group_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
-        for (int i = tid; i < 256 * p.atan_copies; i += TC_THREADS) sT[i] = p.atan_tab[i / p.atan_copies];
-        for (int i = tid; i < p.prog_len; i += TC_THREADS) prog_s[i] = p.prog[i];
-    }
     if (tid == 0) {
         for (int s = 0; s < NB_MAX; s++) { ptx::mbar_init(&b_full[s], (uint32_t)((XF_WARPS - s + p.nb_stages - 1) / p.nb_stages)); ptx::mbar_init(&b_empty[s], MMA_WARPS); }
         for (int s = 0; s < NT_MAX; s++) { ptx::mbar_init(&t_full[s], MMA_WARPS); ptx::mbar_init(&t_empty[s], EPI_WARPS / 2); }
+        ptx::mbar_init(&a_full, 1);
         ptx::fence_mbar_init();
+        /* this group's tap image (the A operand of every MMA of the kernel, 36 - 140 KB) comes in by TMA: one bulk copy
+         * straight into the operand's shared-memory layout, landing while the other threads fill the tables below; the MMA
+         * warps wait for it before their first instruction */
+        ptx::mbar_expect_tx(&a_full, p.a_group_bytes);
+        ptx::bulk_g2s(sA, p.tap_img + (size_t)g * p.a_group_bytes, p.a_group_bytes, &a_full);
+    }
+    {
+        for (int i = tid; i < 256 * p.atan_copies; i += TC_THREADS) sT[i] = p.atan_tab[i / p.atan_copies];
+        for (int i = tid; i < p.prog_len; i += TC_THREADS) prog_s[i] = p.prog[i];
     }
     if (warp_u == MMA_WARP) ptx::tmem_alloc(&tmem_base_s, 512);
     ptx::fence_proxy_async();
@@ -316,6 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
             const bool have0 = i0 + lane < i1;
             if (NFIX == 0 && have0) m0 = prog_s[i0 + lane];
             int sb = 0, phb = 0, st = 0, pht = 0;
+            ptx::mbar_wait(&a_full, 0);                 /* the tap image has landed (also keeps the CTA alive until it has) */
             for (int it = 0; it < my_tiles; it++) {
                 ptx::mbar_wait_backoff(&b_full[sb], phb, SLEEP_MMA);
                 ptx::mbar_wait_backoff(&t_empty[st], pht ^ 1, SLEEP_MMA);

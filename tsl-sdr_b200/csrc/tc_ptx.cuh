@@ -1,6 +1,6 @@
 /*
  * tc_ptx.cuh -- thin inline-PTX wrappers for the sm_100a features the tensor-core engine uses:
- * mbarrier, L2 bulk prefetch (cp.async.bulk.prefetch.L2 -> SASS UBLKPF), TMEM allocation, tcgen05.mma kind::i8
+ * mbarrier, TMA bulk copy (cp.async.bulk -> SASS UBLKCP), L2 bulk prefetch (cp.async.bulk.prefetch.L2 -> SASS UBLKPF), TMEM allocation, tcgen05.mma kind::i8
  * (SASS UTCIMMA), tcgen05.commit, tcgen05.ld (SASS LDTM).
  */
 #pragma once
@@ -66,6 +66,18 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, 
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, uint32_t ns)
 {
     while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
+/* ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP): global -> shared, completion counted in bytes on an mbarrier ---- */
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+/* dst (shared) and src (global) 16-byte aligned, bytes a multiple of 16 */
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 /* ask L2 to fetch [p, p + bytes) (16-byte aligned, multiple of 16) ahead of the loads that will want it */
