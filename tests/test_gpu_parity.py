@@ -141,6 +141,44 @@ def test_long_stream_rot_limit_cycle(oracle, engine):
         assert state[c][4] != 0, "no limit cycle found"
 
 
+@pytest.mark.parametrize("keep_iq", [False, True])
+def test_steady_state_window_tables(oracle, keep_iq):
+    """Tensor-core engine past every channel's transient: the eight derotator phases of a thread's block come from the
+    window tables built from the tabulated limit cycles (filter/direct_fir.c:152-172 is the recurrence they replace).
+    Cycle lengths 1, 2, 3, 4, 6, 8, 12, 15, 24, 200, 262, 356, 524, 600, 772, 1676, 1708 (odd, shorter than a block, not a
+    multiple of 8), ragged submits so that a submit's first output is not a multiple of 8 outputs into the stream, and the
+    launch count shows that the steady-state kernel (one launch per submit, no prepass) really ran."""
+    C, T, D, fs = 17, 16, 4, 2400000
+    offs = np.array([0, 300000, 150000, 75000, 25000, -320000, 50000, 100000, 200000, 7000, 9000, 13000, 59000, 71000, 79000,
+                     29000, 23000], dtype=np.int32)
+    chunks = [600001, 250003, 123457, 77777, 200001, 350013]
+    n = sum(chunks)
+    iq = rand_iq(n, seed=77, amp=9000)
+    lpf = synth.lowpass_taps(T, 100000.0, fs)
+    flags = F_ATAN_FMA | (F_KEEP_IQ if keep_iq else 0)
+    bank = GpuChan(lpf, offs, fs, D, max(chunks), flags=flags, engine=ENGINE_TC)
+    pcm, yiq, per_submit, pos = [], [], [], 0
+    for c in chunks:
+        before = bank.kernel_launches
+        bank.submit(iq[2 * pos: 2 * (pos + c)])
+        pcm.append(bank.collect().copy())
+        if keep_iq:
+            yiq.append(bank.collect_iq().copy())
+        per_submit.append(bank.kernel_launches - before)
+        pos += c
+    cycles = [bank.rot_state(c) for c in range(C)]
+    bank.close()
+    assert per_submit[0] > 1 and per_submit[2:] == [1] * (len(chunks) - 2), per_submit
+    assert len({int(st[4]) for st in cycles}) >= 12, "the offsets no longer give a variety of cycle lengths"
+    pcm = np.concatenate(pcm, axis=1)
+    for c, off in enumerate(offs):
+        y, p = oracle.channel(lpf, off, fs, D, iq)
+        bad = np.flatnonzero(p != pcm[c])
+        assert bad.size == 0, f"channel {c} (offset {off}): first PCM mismatch at output {bad[0]} of {len(p)}"
+        if keep_iq:
+            assert np.array_equal(np.concatenate(yiq, axis=1)[c], y.reshape(-1, 2))
+
+
 def test_taps_match_oracle(oracle, pkg):
     fs, T = 2400000, 127
     lpf = synth.lowpass_taps(T, 9000.0, fs)

@@ -65,7 +65,7 @@ __global__ void atan_selftest_kernel(uint64_t seed, uint64_t per_thread, const f
             Atan2Pair ap2;
             float ex[2], ey[2], phi[2];
             atan2p_stage1(pi_[0], pr_[0], pi_[1], pr_[1], ap2);
-            atan2p_stage2(ap2, tab_biased, 8u, ex, ey);
+            atan2p_stage2<3>(ap2, tab_biased, ex, ey);
             atan2p_stage3<FMA>(pi_[0], pr_[0], pi_[1], pr_[1], ap2, ex, ey, ap.z_small_thr, phi[0], phi[1]);
             float margin = 1.0f;
             int pcm[2];
@@ -151,7 +151,7 @@ __global__ void eval_kernel(const int *__restrict__ s_im, const int *__restrict_
         float ex[2], ey[2], phi[2], margin = 1.0f;
         int pcm[2];
         atan2p_stage1(s_im[i0], s_re[i0], s_im[i1], s_re[i1], a);
-        atan2p_stage2(a, tab_biased, 8u, ex, ey);
+        atan2p_stage2<3>(a, tab_biased, ex, ey);
         atan2p_stage3<FMA>(s_im[i0], s_re[i0], s_im[i1], s_re[i1], a, ex, ey, z_thr, phi[0], phi[1]);
         pcm_from_phi_pair(phi[0], phi[1], margin, pcm[0], pcm[1]);
         if (margin < 0.0f) { pcm[0] = pcm_from_phi_exact(__fmul_rn(phi[0], 16384.0f)); pcm[1] = pcm_from_phi_exact(__fmul_rn(phi[1], 16384.0f)); }

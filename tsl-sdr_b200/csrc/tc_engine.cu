@@ -44,20 +44,19 @@ namespace tslb200 {
 namespace {
 
 constexpr int EPI_WARPS = 16;
-#ifndef TC_XF_WARPS
-#define TC_XF_WARPS 8
-#endif
-constexpr int XF_WARPS = TC_XF_WARPS;   /* transform warps: raw cs16 -> byte planes in smem */
-constexpr int XF_THREADS = 32 * XF_WARPS;
-/* The transform warps form one group per sample stage (warp w -> group w % NB); a group fills its stage on its own,
- * so NB tiles' loads are in flight at any time.  One group per stage also keeps every barrier wait at most one
- * phase behind (a parity wait cannot tell phases two apart). */
+/* Transform warps (raw cs16 -> byte planes in smem) are a kernel template parameter XF.  They form one group per sample
+ * stage (warp w -> group w % NB); a group fills its stage on its own, so NB tiles' loads are in flight at any time.  One
+ * group per stage also keeps every barrier wait at most one phase behind (a parity wait cannot tell phases two apart).
+ * Measured on B200 (profiles/r02_xf_warps_experiment.txt): with several channel groups per sample tile (the groups' CTAs
+ * find the tile in L2) 6 warps are enough and leave the epilogue 80 registers and more issue slots (256 channels x 127
+ * taps: 0.273 ms against 0.285 with 8); with one group the tiles come from HBM and 8 warps are faster (64 channels: 0.088
+ * against 0.090 ms); 5 warps (groups of 2, 2, 1) lose 25 %. */
+constexpr int XF_MANY_GROUPS = 6, XF_ONE_GROUP = 8;
 /* Warp roles, lowest warp index first: epilogue | transform | MMA issuer. */
 constexpr int EPI_WARP0 = 0;            /* must be a multiple of 4: warp w may only read TMEM lanes 32*(w%4).. */
 constexpr int XF_WARP0 = EPI_WARPS;     /* first transform warp */
 constexpr int MMA_WARPS = 2;            /* MMA issuers (2 = each owns a disjoint set of limb accumulators) */
-constexpr int MMA_WARP = EPI_WARPS + XF_WARPS;      /* warp index of the first MMA issuer */
-constexpr int TC_THREADS = 32 * (XF_WARPS + MMA_WARPS + EPI_WARPS);
+__host__ __device__ constexpr int tc_threads(int xf) { return 32 * (xf + MMA_WARPS + EPI_WARPS); }
 constexpr int NB_MAX = 4, NT_MAX = 3;
 /* nanoseconds between polls of a role's barrier wait (measured on B200: shorter intervals spend issue slots the epilogue
  * needs, longer ones add latency to the hand-offs; hardware-suspended try_wait was no faster) */
@@ -125,9 +124,13 @@ __device__ __forceinline__ void split_store(const uint32_t (&w)[8], uint8_t *hi_
 }
 
 
-template <int MODE, bool KEEP_IQ, bool FMA>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_constant__ TcKernelParams p)
+/* ATAN16: 16 interleaved copies of the arctangent table in shared memory (else one) */
+template <int MODE, bool KEEP_IQ, bool FMA, bool ATAN16, int XF_WARPS>
+__global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(const __grid_constant__ TcKernelParams p)
 {
+    constexpr int XF_THREADS = 32 * XF_WARPS;
+    constexpr int MMA_WARP = EPI_WARPS + XF_WARPS;              /* warp index of the first MMA issuer */
+    constexpr int TC_THREADS = tc_threads(XF_WARPS);
     constexpr int ACCS = (MODE == TC_MODE_SUM) ? 2 : 3;
     constexpr int NT = 512 / (ACCS * TC_ACC_STRIDE);            /* TMEM stages: 3 (SUM) or 2 (RADIX) */
     constexpr uint32_t STAGE_COLS = ACCS * TC_ACC_STRIDE;
@@ -398,8 +401,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
         short *const pcm_c = p.pcm + (size_t)c * p.pitch;
         int *const iq_c = KEEP_IQ ? p.iq_out + (size_t)c * p.pitch : nullptr;
         const float z_thr = p.atan.z_small_thr;
-        const uint32_t atan_mul = 8u * (uint32_t)p.atan_copies;
-        const uint32_t atan_smem = ptx::smem_u32(sT) + 8u * ((uint32_t)lane & (uint32_t)(p.atan_copies - 1)) - 0x4B000000u * atan_mul;
+        constexpr int ATAN_SHIFT = ATAN16 ? 7 : 3;                  /* bytes between entries of one copy: 8 * copies */
+        const uint32_t atan_smem = ptx::smem_u32(sT) + 8u * ((uint32_t)lane & (uint32_t)(p.atan_copies - 1)) - (0x4B000000u << ATAN_SHIFT);
         /* Steady state (every channel on its limit cycle): the phase of the output before my first one comes from the
          * channel's cycle table; it advances by 2 * TC_OUT outputs from one of my tiles to the next. */
         const bool table_mode = p.ckpt == nullptr;
@@ -528,7 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_fir_fm_kernel(const __grid_c
 #pragma unroll
                             for (int q = 0; q < 2; q++) atan2p_stage1(sim[2 * q], sre[2 * q], sim[2 * q + 1], sre[2 * q + 1], as[q]);
 #pragma unroll
-                            for (int q = 0; q < 2; q++) atan2p_stage2(as[q], atan_smem, atan_mul, ex[q], ey[q]);
+                            for (int q = 0; q < 2; q++) atan2p_stage2<ATAN_SHIFT>(as[q], atan_smem, ex[q], ey[q]);
 #pragma unroll
                             for (int q = 0; q < 2; q++)
                                 atan2p_stage3<FMA>(sim[2 * q], sre[2 * q], sim[2 * q + 1], sre[2 * q + 1], as[q], ex[q], ey[q], z_thr,
@@ -754,19 +757,27 @@ size_t tc_max_ckpt_tiles(const TcPlan &, long long max_K, int)
     return (size_t)(max_K / TC_OUT + 2);
 }
 
-template <int MODE, bool KEEP_IQ, bool FMA>
+template <int MODE, bool KEEP_IQ, bool FMA, bool ATAN16, int XF>
 static cudaError_t launch_variant(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(tc_fir_fm_kernel<MODE, KEEP_IQ, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_fir_fm_kernel<MODE, KEEP_IQ, FMA, ATAN16, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_fir_fm_kernel<MODE, KEEP_IQ, FMA><<<ctas, TC_THREADS, smem, st>>>(p);
+    tc_fir_fm_kernel<MODE, KEEP_IQ, FMA, ATAN16, XF><<<ctas, tc_threads(XF), smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int MODE, bool KEEP_IQ>
-static cudaError_t launch_variant2(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st, bool fma)
+template <int MODE, bool KEEP_IQ, bool FMA>
+static cudaError_t launch_variant3(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st, bool atan16, bool many_groups)
 {
-    return fma ? launch_variant<MODE, KEEP_IQ, true>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, false>(p, ctas, smem, st);
+    if (many_groups)
+        return atan16 ? launch_variant<MODE, KEEP_IQ, FMA, true, XF_MANY_GROUPS>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, FMA, false, XF_MANY_GROUPS>(p, ctas, smem, st);
+    return atan16 ? launch_variant<MODE, KEEP_IQ, FMA, true, XF_ONE_GROUP>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, FMA, false, XF_ONE_GROUP>(p, ctas, smem, st);
+}
+
+template <int MODE, bool KEEP_IQ>
+static cudaError_t launch_variant2(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st, bool fma, bool atan16, bool many_groups)
+{
+    return fma ? launch_variant3<MODE, KEEP_IQ, true>(p, ctas, smem, st, atan16, many_groups) : launch_variant3<MODE, KEEP_IQ, false>(p, ctas, smem, st, atan16, many_groups);
 }
 
 cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st)
@@ -791,9 +802,10 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     const bool iq = b.iq_out != nullptr, fma = b.atan.use_fma != 0;
     p.atan_copies = pl.atan_copies;
     const size_t sm = pl.smem_bytes;
+    const bool a16 = pl.atan_copies == 16, mg = pl.G >= 2;
     if (pl.mode == TC_MODE_RADIX)
-        return iq ? launch_variant2<TC_MODE_RADIX, true>(p, ctas, sm, st, fma) : launch_variant2<TC_MODE_RADIX, false>(p, ctas, sm, st, fma);
-    return iq ? launch_variant2<TC_MODE_SUM, true>(p, ctas, sm, st, fma) : launch_variant2<TC_MODE_SUM, false>(p, ctas, sm, st, fma);
+        return iq ? launch_variant2<TC_MODE_RADIX, true>(p, ctas, sm, st, fma, a16, mg) : launch_variant2<TC_MODE_RADIX, false>(p, ctas, sm, st, fma, a16, mg);
+    return iq ? launch_variant2<TC_MODE_SUM, true>(p, ctas, sm, st, fma, a16, mg) : launch_variant2<TC_MODE_SUM, false>(p, ctas, sm, st, fma, a16, mg);
 }
 
 } // namespace tslb200
