@@ -58,9 +58,20 @@ constexpr int XF_WARP0 = EPI_WARPS;     /* first transform warp */
 constexpr int MMA_WARPS = 2;            /* MMA issuers (2 = each owns a disjoint set of limb accumulators) */
 __host__ __device__ constexpr int tc_threads(int xf) { return 32 * (xf + MMA_WARPS + EPI_WARPS); }
 constexpr int NB_MAX = 4, NT_MAX = 3;
+/* TC_DIAG (diagnostics builds only, `make diag`; results are wrong by design): bit 0 = no epilogue arithmetic (the PCM
+ * stores write the raw accumulator words), bit 1 = no transform (the MMAs read whatever the sample stages hold), bit 2 = one
+ * MMA per issuing warp and tile.  Timing such builds attributes the tile time to the three roles. */
+#ifndef TC_DIAG
+#define TC_DIAG 0
+#endif
 /* nanoseconds between polls of a role's barrier wait (measured on B200: shorter intervals spend issue slots the epilogue
  * needs, longer ones add latency to the hand-offs; hardware-suspended try_wait was no faster) */
-constexpr uint32_t SLEEP_EPI = 200, SLEEP_XF = 1000, SLEEP_MMA = 100;
+#ifndef TC_SLEEP_EPI
+#define TC_SLEEP_EPI 200
+#define TC_SLEEP_XF 1000
+#define TC_SLEEP_MMA 100
+#endif
+constexpr uint32_t SLEEP_EPI = TC_SLEEP_EPI, SLEEP_XF = TC_SLEEP_XF, SLEEP_MMA = TC_SLEEP_MMA;
 
 /* ---------------------------------------------------------------------------------------------- */
 struct TcKernelParams {
@@ -221,7 +232,8 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
             const long long row_base = (long long)TC_OUT * (tile0 + it) - TC_LEAD;
             const long long s_first = row_base * (long long)p.D;
             const long long s_last = s_first + (long long)(p.R - 1) * p.D + 8 * nslab + 12;     /* one past the furthest word read */
-            if (s_first >= p.in.carry_len + 4 && s_last <= p.in.total) {
+            if (TC_DIAG & 2) {
+            } else if (s_first >= p.in.carry_len + 4 && s_last <= p.in.total) {
                 /* a thread keeps one slab column j and walks down the rows: addresses advance by constants, and the
                  * loads of consecutive rows are independent, so several stay in flight */
                 const int *base = p.in.fresh + (s_first - p.in.carry_len);
@@ -333,7 +345,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
                     if (ptx::elect_one()) {
 #pragma unroll
                         for (int i = 0; i < NARR; i++) {
-                            if (i < n_mine)
+                            if (i < ((TC_DIAG & 4) ? 1 : n_mine))
                                 ptx::mma_i8(acc + ((i & 1) ? d_odd : d_even), ((uint64_t)DESC_HI << 32) | (uint64_t)fa[i],
                                             ((uint64_t)DESC_HI << 32) | (uint64_t)(fb[i] + b_base), (i & 1) ? i_odd : i_even,
                                             (i == 0 || (i == 1 && odd_is_new_acc)) ? 0u : 1u);
@@ -396,6 +408,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
         const uint32_t lane_re = (uint32_t)(32 * slice) << 16, lane_im = (uint32_t)(32 * slice + 16) << 16;
         const int c = g * TC_CH + ch;
         const bool live = c < p.C;
+        const int K32 = (int)p.K;                   /* outputs per channel of this submit (tc_launch_fir_fm checks the range) */
         const int iw = live ? __ldg(p.incr + c) : 0;
         const int i4_re = 4 * lo16(iw), i4_im = 4 * hi16(iw);
         short *const pcm_c = p.pcm + (size_t)c * p.pitch;
@@ -421,7 +434,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
         auto phase_word = [&](int it) -> int {
             if (!live) return 0;
             const int tile = tile0 + it;
-            if (!table_mode && (long long)TC_OUT * tile + 8 * blk0 >= p.K) return 0;   /* block past the last output: its
+            if (!table_mode && TC_OUT * tile + 8 * blk0 >= K32) return 0;   /* block past the last output: its
                                                                                           checkpoint was never written */
             if (table_mode) {
                 uint32_t ix = tph;
@@ -471,7 +484,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
 #pragma unroll 1
             for (int b = 0; b < 2; b++) {
                 int x_re[8], x_im[8];
-                const long long kfirst = (long long)TC_OUT * tile + 8 * (blk0 + b);     /* output index of the block's first column */
+                const int kfirst = TC_OUT * tile + 8 * (blk0 + b);     /* output index of the block's first column (a submit has < 2^31 outputs) */
                 if (b == 0) {
                     /* the column before the first block: the discriminator's previous sample */
                     int l0r, l1r, l2r = 0, l0i, l1i, l2i = 0;
@@ -502,8 +515,15 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
                 }
 
                 /* ---- one channel x 8 consecutive outputs ---- */
-                const int nvalid = (p.K - kfirst > 8) ? 8 : (int)(p.K - kfirst);
-                if (live && nvalid > 0) {
+                const int nvalid = (K32 - kfirst > 8) ? 8 : K32 - kfirst;
+                if (TC_DIAG & 1) {
+                    if (live && kfirst + 8 < K32) {
+                        int acc = 0;
+#pragma unroll
+                        for (int u = 0; u < 8; u++) acc ^= x_re[u] + x_im[u];
+                        *reinterpret_cast<uint4 *>(pcm_c + kfirst) = make_uint4((uint32_t)acc, (uint32_t)x_re[0], (uint32_t)x_im[1], (uint32_t)r_re);
+                    }
+                } else if (live && nvalid > 0) {
                     /* EDGE = this block holds the submit's last output (or is cut short by it): also track y[K-1] */
                     auto block8 = [&](auto edge_tag) {
                         constexpr bool EDGE = decltype(edge_tag)::value;
@@ -557,9 +577,9 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
                                 if (u < nvalid) pcm_c[kfirst + u] = (short)(out[u >> 1] >> (16 * (u & 1)));
                         }
                         /* the thread that produced the submit's last output hands y[K-1] to the next submit */
-                        if (EDGE) { if (kfirst + nvalid == p.K) p.last_out[c] = pack16(l_re, l_im); }
+                        if (EDGE) { if (kfirst + nvalid == K32) p.last_out[c] = pack16(l_re, l_im); }
                     };
-                    if (kfirst + 8 < p.K) block8(std::false_type{});
+                    if (kfirst + 8 < K32) block8(std::false_type{});
                     else block8(std::true_type{});
                 }
             }
@@ -783,6 +803,7 @@ static cudaError_t launch_variant2(const TcKernelParams &p, unsigned ctas, size_
 cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st)
 {
     if (b.geom.chunks <= 0) return cudaSuccess;
+    if (b.K >= (1ull << 31) - 2 * TC_OUT) return cudaErrorInvalidValue;     /* the kernel indexes a submit's outputs with int */
     TcKernelParams p;
     memset(&p, 0, sizeof(p));
     p.in = b.in; p.D = pl.D;
