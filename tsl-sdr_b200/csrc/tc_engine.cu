@@ -36,6 +36,7 @@
 #include "tc_ptx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -50,7 +51,8 @@ constexpr int EPI_WARPS = 16;
  * Measured on B200 (profiles/r02_xf_warps_experiment.txt): with several channel groups per sample tile (the groups' CTAs
  * find the tile in L2) 6 warps are enough and leave the epilogue 80 registers and more issue slots (256 channels x 127
  * taps: 0.273 ms against 0.285 with 8); with one group the tiles come from HBM and 8 warps are faster (64 channels: 0.088
- * against 0.090 ms); 5 warps (groups of 2, 2, 1) lose 25 %. */
+ * against 0.090 ms); 5 warps (groups of 2, 2, 1) lose 25 %.  With two channel groups per CTA (a sample tile transformed
+ * once for both): 4 / 5 / 6 warps 0.2548 / 0.2520 / 0.2503 ms. */
 constexpr int XF_MANY_GROUPS = 6, XF_ONE_GROUP = 8;
 /* Warp roles, lowest warp index first: epilogue | transform | MMA issuer. */
 constexpr int EPI_WARP0 = 0;            /* must be a multiple of 4: warp w may only read TMEM lanes 32*(w%4).. */
@@ -95,6 +97,7 @@ struct TcKernelParams {
     int n_tiles;            /* tiles per CTA */
     int total_tiles;
     int C, G, Kp, Q, R;
+    int gpc;                /* channel groups per CTA: 1, or 2 sharing every transformed sample tile (one epilogue set each) */
     int nb_stages, prog_len, prog_split, prog_regular;
     int atan_copies;        /* interleaved copies of the arctangent table in shared memory: 16 or 1 */
     uint32_t a_group_bytes, b_stage_bytes;
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
     __shared__ TcMma prog_s[TC_PROG_MAX];
 
     uint8_t *sA = smem;                                         /* [a_chunks][2 slabs][128][16] */
-    uint8_t *sB = smem + p.a_group_bytes;                       /* [NB stages][2 planes][nslab][R][16] */
+    uint8_t *sB = smem + (size_t)p.gpc * p.a_group_bytes;       /* [NB stages][2 planes][nslab][R][16] */
     /* arctangent table, entry-major with atan_copies (16 or 1) interleaved copies: entry i of copy c sits at
      * (i * copies + c) * 8 bytes, so that with 16 copies lane l (copy l & 15) always reads bank pair l & 15 -- every
      * table load is two conflict-free wavefronts.  (One shared copy cost 12.8 wavefronts per load on average: the
@@ -161,8 +164,10 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);       /* same value, but provably warp-uniform for the compiler */
     const int nslab = p.Kp >> 4;
     const int NB = p.nb_stages;
-    const int g = blockIdx.x % p.G;                             /* channel group of this CTA */
-    const int chunk = blockIdx.x / p.G;
+    const int gpc = p.gpc;
+    const int cta_groups = p.G / gpc;                           /* CTAs per tile range */
+    const int g = (blockIdx.x % cta_groups) * gpc;              /* (first) channel group of this CTA */
+    const int chunk = blockIdx.x / cta_groups;
     const int tile0 = chunk * p.n_tiles;                        /* first tile of this CTA */
     int my_tiles = p.total_tiles - tile0;
     if (my_tiles > p.n_tiles) my_tiles = p.n_tiles;
@@ -186,15 +191,15 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
 
     /* ---- one-time setup ---- */
     if (tid == 0) {
-        for (int s = 0; s < NB_MAX; s++) { ptx::mbar_init(&b_full[s], (uint32_t)((XF_WARPS - s + p.nb_stages - 1) / p.nb_stages)); ptx::mbar_init(&b_empty[s], MMA_WARPS); }
+        for (int s = 0; s < NB_MAX; s++) { ptx::mbar_init(&b_full[s], (uint32_t)((XF_WARPS - s + p.nb_stages - 1) / p.nb_stages)); ptx::mbar_init(&b_empty[s], (uint32_t)(MMA_WARPS * p.gpc)); }
         for (int s = 0; s < NT_MAX; s++) { ptx::mbar_init(&t_full[s], MMA_WARPS); ptx::mbar_init(&t_empty[s], EPI_WARPS / 2); }
         ptx::mbar_init(&a_full, 1);
         ptx::fence_mbar_init();
         /* this group's tap image (the A operand of every MMA of the kernel, 36 - 140 KB) comes in by TMA: one bulk copy
          * straight into the operand's shared-memory layout, landing while the other threads fill the tables below; the MMA
          * warps wait for it before their first instruction */
-        ptx::mbar_expect_tx(&a_full, p.a_group_bytes);
-        ptx::bulk_g2s(sA, p.tap_img + (size_t)g * p.a_group_bytes, p.a_group_bytes, &a_full);
+        ptx::mbar_expect_tx(&a_full, (uint32_t)gpc * p.a_group_bytes);
+        ptx::bulk_g2s(sA, p.tap_img + (size_t)g * p.a_group_bytes, (uint32_t)gpc * p.a_group_bytes, &a_full);
     }
     {
         for (int i = tid; i < 256 * p.atan_copies; i += TC_THREADS) sT[i] = p.atan_tab[i / p.atan_copies];
@@ -335,18 +340,24 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
             if (NFIX == 0 && have0) m0 = prog_s[i0 + lane];
             int sb = 0, phb = 0, st = 0, pht = 0;
             ptx::mbar_wait(&a_full, 0);                 /* the tap image has landed (also keeps the CTA alive until it has) */
-            for (int it = 0; it < my_tiles; it++) {
+            /* With two channel groups per CTA every sample stage is used twice in a row -- "virtual tile" v = 2 * tile + group:
+             * same B operand, the other group's tap image, the next accumulator stage -- and released after the second use. */
+            const uint32_t a_group16 = p.a_group_bytes >> 4;
+            const int n_virtual = my_tiles * gpc;
+            for (int v = 0; v < n_virtual; v++) {
+                const bool second = gpc == 2 && (v & 1);
                 ptx::mbar_wait_backoff(&b_full[sb], phb, SLEEP_MMA);
                 ptx::mbar_wait_backoff(&t_empty[st], pht ^ 1, SLEEP_MMA);
                 ptx::tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)st * STAGE_COLS;
                 const uint32_t b_base = b_base0 + (((uint32_t)sb * p.b_stage_bytes) >> 4);
+                const uint32_t a_off = second ? a_group16 : 0u;
                 if (NFIX > 0) {
                     if (ptx::elect_one()) {
 #pragma unroll
                         for (int i = 0; i < NARR; i++) {
                             if (i < ((TC_DIAG & 4) ? 1 : n_mine))
-                                ptx::mma_i8(acc + ((i & 1) ? d_odd : d_even), ((uint64_t)DESC_HI << 32) | (uint64_t)fa[i],
+                                ptx::mma_i8(acc + ((i & 1) ? d_odd : d_even), ((uint64_t)DESC_HI << 32) | (uint64_t)(fa[i] + a_off),
                                             ((uint64_t)DESC_HI << 32) | (uint64_t)(fb[i] + b_base), (i & 1) ? i_odd : i_even,
                                             (i == 0 || (i == 1 && odd_is_new_acc)) ? 0u : 1u);
                         }
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
                             have = i0 + 32 * ps + lane < i1;
                             if (have) m = prog_s[i0 + 32 * ps + lane];
                         }
-                        const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.a_lo + a_base);
+                        const uint64_t da = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.a_lo + a_base + a_off);
                         const uint64_t db = ((uint64_t)DESC_HI << 32) | (uint64_t)(m.b_lo + b_base);
                         const uint32_t d = acc + (m.d_acc & 0xffffu);
                         const bool first = (m.d_acc >> 31) == 0;
@@ -378,7 +389,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
                     ptx::mma_commit(&t_full[st]);       /* accumulators complete */
                 }
                 __syncwarp();
-                if (++sb == NB) { sb = 0; phb ^= 1; }
+                if (gpc == 1 || second) { if (++sb == NB) { sb = 0; phb ^= 1; } }
                 if (++st == NT) { st = 0; pht ^= 1; }
             }
         };
@@ -406,7 +417,9 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
         const int ch = 16 * slice + (lane & 15);
         const int blk0 = 4 * half + (hi ? 2 : 0);   /* first of this thread's two 8-output blocks of a tile */
         const uint32_t lane_re = (uint32_t)(32 * slice) << 16, lane_im = (uint32_t)(32 * slice + 16) << 16;
-        const int c = g * TC_CH + ch;
+        /* one group per CTA: the two sets take alternate tiles; two groups: set s owns group g + s and takes every tile */
+        const int t_first = gpc == 2 ? 0 : set, t_step = gpc == 2 ? 1 : 2;
+        const int c = (g + (gpc == 2 ? set : 0)) * TC_CH + ch;
         const bool live = c < p.C;
         const int K32 = (int)p.K;                   /* outputs per channel of this submit (tc_launch_fir_fm checks the range) */
         const int iw = live ? __ldg(p.incr + c) : 0;
@@ -417,15 +430,15 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
         constexpr int ATAN_SHIFT = ATAN16 ? 7 : 3;                  /* bytes between entries of one copy: 8 * copies */
         const uint32_t atan_smem = ptx::smem_u32(sT) + 8u * ((uint32_t)lane & (uint32_t)(p.atan_copies - 1)) - (0x4B000000u << ATAN_SHIFT);
         /* Steady state (every channel on its limit cycle): the phase of the output before my first one comes from the
-         * channel's cycle table; it advances by 2 * TC_OUT outputs from one of my tiles to the next. */
+         * channel's cycle table; it advances by t_step * TC_OUT outputs from one of my tiles to the next. */
         const bool table_mode = p.ckpt == nullptr;
         uint32_t lam = 1, tph = 0, tstep = 0;
         const int *tab = nullptr;
         if (table_mode && live) {
             lam = __ldg(p.lambda + c);
-            const unsigned long long g0 = p.k_base + (unsigned long long)TC_OUT * (tile0 + set) + 8 * blk0 - 1 - __ldg(p.mu + c);
+            const unsigned long long g0 = p.k_base + (unsigned long long)TC_OUT * (tile0 + t_first) + 8 * blk0 - 1 - __ldg(p.mu + c);
             tph = (uint32_t)(g0 % lam);
-            tstep = (uint32_t)(2 * TC_OUT) % lam;
+            tstep = (uint32_t)(t_step * TC_OUT) % lam;
             tab = p.cyc + (size_t)c * p.cyc_pitch;
         }
         /* derotator phase word of tile `it` of this CTA: the phase of the output before my first block (of output 0
@@ -445,11 +458,12 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
             }
             return __ldg(p.ckpt + ((size_t)tile * TC_SUB + blk0) * p.C + c);
         };
-        int cwk_next = set < my_tiles ? phase_word(set) : 0;
+        int cwk_next = t_first < my_tiles ? phase_word(t_first) : 0;
 
-        for (int it = set; it < my_tiles; it += 2) {
+        for (int it = t_first; it < my_tiles; it += t_step) {
             const int tile = tile0 + it;
-            const int st = it % NT, pht = (it / NT) & 1;
+            const int v = gpc == 2 ? 2 * it + set : it;         /* virtual tile: which accumulator stage holds it */
+            const int st = v % NT, pht = (v / NT) & 1;
             const int cwk = cwk_next;
             ptx::mbar_wait_backoff(&t_full[st], pht, SLEEP_EPI);
             ptx::tc_fence_after();
@@ -497,7 +511,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
                         ptx::tmem_ld1_split16(col0 - 1 + lane_im + 2 * TC_ACC_STRIDE, l2i);
                     }
                     drain8(col0, x_re, x_im);
-                    if (it + 2 < my_tiles) cwk_next = phase_word(it + 2);
+                    if (it + t_step < my_tiles) cwk_next = phase_word(it + t_step);
                     if (kfirst == 0) {
                         /* very first output of the submit: y[-1] is carried state; the phase word = phase of output 0 */
                         const int lw = live ? __ldg(p.last_in + c) : 0;
@@ -712,18 +726,33 @@ TcPlan tc_make_plan(int T, int D, int C, const int16_t *c_re, const int16_t *c_i
     pl.a_group_bytes = (size_t)pl.a_chunks * 4096;
     pl.b_stage_bytes = (size_t)2 * pl.Kp * pl.R;
     const size_t static_smem = 2560 + 512;     /* MMA program, barriers, slack */
-    /* 16 interleaved copies of the arctangent table (32 KB) if at least 3 sample stages still fit, else one (2 KB) */
+    /* Two channel groups per CTA whenever both tap images, two sample stages and the 16 arctangent copies fit: a sample
+     * tile is then transformed once for both groups (each epilogue set owns one of them) -- the transform, which paces the
+     * kernel as much as the epilogue does (diagnostics builds), costs half as much per output.
+     * Otherwise one group per CTA with 16 interleaved copies of the arctangent table (32 KB) if at least 3 sample stages
+     * still fit, else one copy (2 KB). */
     long long nb = 0;
-    for (int copies = 16; copies >= 1; copies /= 16) {
-        const long long room = (long long)smem_max - (long long)static_smem - (long long)pl.a_group_bytes - 128 - 2048LL * copies;
+    pl.gpc = 1;
+    const char *gpc_env = getenv("GPUCHAN_TC_GPC");            /* measurement knob: GPUCHAN_TC_GPC=1 keeps one group per CTA */
+    const bool may_pair = !(gpc_env && atoi(gpc_env) == 1);
+    if (may_pair && pl.G % 2 == 0 && (pl.a_chunks * 2) * 256 < 16384) {
+        const long long room = (long long)smem_max - (long long)static_smem - 2 * (long long)pl.a_group_bytes - 128 - 2048LL * 16;
         nb = room / (long long)pl.b_stage_bytes;
         if (nb > NB_MAX) nb = NB_MAX;
-        pl.atan_copies = copies;
-        if (nb >= 3) break;
+        if (nb >= 2) { pl.gpc = 2; pl.atan_copies = 16; }
+    }
+    if (pl.gpc == 1) {
+        for (int copies = 16; copies >= 1; copies /= 16) {
+            const long long room = (long long)smem_max - (long long)static_smem - (long long)pl.a_group_bytes - 128 - 2048LL * copies;
+            nb = room / (long long)pl.b_stage_bytes;
+            if (nb > NB_MAX) nb = NB_MAX;
+            pl.atan_copies = copies;
+            if (nb >= 3) break;
+        }
     }
     if (nb < 2) { pl.why = "tap image + sample ring exceed shared memory"; return pl; }
     pl.nb_stages = (int)nb;
-    pl.smem_bytes = pl.a_group_bytes + (size_t)pl.nb_stages * pl.b_stage_bytes + 2048 * (size_t)pl.atan_copies + 128;
+    pl.smem_bytes = (size_t)pl.gpc * pl.a_group_bytes + (size_t)pl.nb_stages * pl.b_stage_bytes + 2048 * (size_t)pl.atan_copies + 128;
     if ((size_t)pl.R * 16 >= (1u << 18)) { pl.why = "tile too tall for the descriptor"; return pl; }
     pl.ok = true;
     return pl;
@@ -764,7 +793,7 @@ TcGeom tc_geometry(const TcPlan &pl, long long K, int nr_sms)
     TcGeom gm;
     if (K <= 0) return gm;
     gm.total_tiles = (int)((K + TC_OUT - 1) / TC_OUT);
-    long long ctas = nr_sms / pl.G;
+    long long ctas = nr_sms / (pl.G / pl.gpc);
     if (ctas < 1) ctas = 1;
     if (ctas > gm.total_tiles) ctas = gm.total_tiles;
     gm.n_tiles = (int)((gm.total_tiles + ctas - 1) / ctas);
@@ -812,14 +841,14 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     p.carry_out = b.carry_out; p.carry_from = b.carry_from; p.carry_keep = b.carry_keep;
     p.atan_tab = b.atan_tab; p.pcm = b.pcm; p.iq_out = b.iq_out; p.pitch = b.pitch; p.K = (long long)b.K;
     p.n_tiles = b.geom.n_tiles; p.total_tiles = b.geom.total_tiles;
-    p.C = pl.C; p.G = pl.G; p.Kp = pl.Kp; p.Q = pl.Q; p.R = pl.R;
+    p.C = pl.C; p.G = pl.G; p.Kp = pl.Kp; p.Q = pl.Q; p.R = pl.R; p.gpc = pl.gpc;
     p.nb_stages = pl.nb_stages; p.prog_len = (int)pl.prog.size(); p.prog_split = pl.prog_split;
     p.prog_regular = pl.prog_regular ? 1 : 0;
     p.a_group_bytes = (uint32_t)pl.a_group_bytes; p.b_stage_bytes = (uint32_t)pl.b_stage_bytes;
     p.atan = b.atan;
     memcpy(p.prog, pl.prog.data(), pl.prog.size() * sizeof(TcMma));
     /* persistent grid: one CTA per (tile range, channel group), at most one per SM */
-    const unsigned ctas = (unsigned)b.geom.chunks * (unsigned)pl.G;
+    const unsigned ctas = (unsigned)b.geom.chunks * (unsigned)(pl.G / pl.gpc);
     const bool iq = b.iq_out != nullptr, fma = b.atan.use_fma != 0;
     p.atan_copies = pl.atan_copies;
     const size_t sm = pl.smem_bytes;

@@ -39,6 +39,7 @@ struct TcPlan {
     int Q = 0;                          /* block-rows spanned by the filter: ceil(T / D) */
     int R = 0;                          /* plane rows per tile: TC_N + Q - 1 */
     int G = 0;                          /* channel groups of TC_CH */
+    int gpc = 1;                        /* channel groups per CTA (2: a transformed sample tile feeds two groups' MMAs) */
     int mode = TC_MODE_RADIX;           /* how int16 taps are made of int8 operands */
     int accs = 3;                       /* limb accumulators per TMEM stage (SUM: 2, RADIX: 3) */
     int nb_stages = 2;                  /* sample stages in shared memory */
