@@ -48,12 +48,11 @@ constexpr int EPI_WARPS = 16;
 /* Transform warps (raw cs16 -> byte planes in smem) are a kernel template parameter XF.  They form one group per sample
  * stage (warp w -> group w % NB); a group fills its stage on its own, so NB tiles' loads are in flight at any time.  One
  * group per stage also keeps every barrier wait at most one phase behind (a parity wait cannot tell phases two apart).
- * Measured on B200 (profiles/r02_xf_warps_experiment.txt): with several channel groups per sample tile (the groups' CTAs
- * find the tile in L2) 6 warps are enough and leave the epilogue 80 registers and more issue slots (256 channels x 127
- * taps: 0.273 ms against 0.285 with 8); with one group the tiles come from HBM and 8 warps are faster (64 channels: 0.088
- * against 0.090 ms); 5 warps (groups of 2, 2, 1) lose 25 %.  With two channel groups per CTA (a sample tile transformed
- * once for both): 4 / 5 / 6 warps 0.2548 / 0.2520 / 0.2503 ms. */
-constexpr int XF_MANY_GROUPS = 6, XF_ONE_GROUP = 8;
+ * Measured on B200 (profiles/r02_xf_warps_experiment.txt): when a transformed tile serves two channel groups (TcPlan::gpc
+ * = 2) 6 warps are enough and leave the epilogue 80 registers (256 channels x 127 taps: 4 / 5 / 6 / 8 warps 0.2548 / 0.2520 /
+ * 0.2493 / 0.2559 ms); with one group per CTA 8 warps are faster (64 channels: 0.088 against 0.090 ms; 1024 channels x 255
+ * taps, D = 200: 0.822 against 0.861; 256 x 512 taps: 0.348 against 0.367); 5 warps in groups of 2, 2, 1 lose 25 %. */
+constexpr int XF_PAIRED = 6, XF_ONE_GROUP = 8;
 /* Warp roles, lowest warp index first: epilogue | transform | MMA issuer. */
 constexpr int EPI_WARP0 = 0;            /* must be a multiple of 4: warp w may only read TMEM lanes 32*(w%4).. */
 constexpr int XF_WARP0 = EPI_WARPS;     /* first transform warp */
@@ -819,7 +818,7 @@ template <int MODE, bool KEEP_IQ, bool FMA>
 static cudaError_t launch_variant3(const TcKernelParams &p, unsigned ctas, size_t smem, cudaStream_t st, bool atan16, bool many_groups)
 {
     if (many_groups)
-        return atan16 ? launch_variant<MODE, KEEP_IQ, FMA, true, XF_MANY_GROUPS>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, FMA, false, XF_MANY_GROUPS>(p, ctas, smem, st);
+        return atan16 ? launch_variant<MODE, KEEP_IQ, FMA, true, XF_PAIRED>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, FMA, false, XF_PAIRED>(p, ctas, smem, st);
     return atan16 ? launch_variant<MODE, KEEP_IQ, FMA, true, XF_ONE_GROUP>(p, ctas, smem, st) : launch_variant<MODE, KEEP_IQ, FMA, false, XF_ONE_GROUP>(p, ctas, smem, st);
 }
 
@@ -852,7 +851,11 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     const bool iq = b.iq_out != nullptr, fma = b.atan.use_fma != 0;
     p.atan_copies = pl.atan_copies;
     const size_t sm = pl.smem_bytes;
-    const bool a16 = pl.atan_copies == 16, mg = pl.G >= 2;
+    /* 6 transform warps (80 registers for the epilogue) when a transformed tile serves two groups, 8 otherwise (measured:
+     * profiles/r02_xf_warps_experiment.txt).  GPUCHAN_TC_XF=6|8 overrides the choice for measurements. */
+    bool mg = pl.gpc == 2;
+    if (const char *e = getenv("GPUCHAN_TC_XF")) { if (atoi(e) == 6) mg = true; else if (atoi(e) == 8) mg = false; }
+    const bool a16 = pl.atan_copies == 16;
     if (pl.mode == TC_MODE_RADIX)
         return iq ? launch_variant2<TC_MODE_RADIX, true>(p, ctas, sm, st, fma, a16, mg) : launch_variant2<TC_MODE_RADIX, false>(p, ctas, sm, st, fma, a16, mg);
     return iq ? launch_variant2<TC_MODE_SUM, true>(p, ctas, sm, st, fma, a16, mg) : launch_variant2<TC_MODE_SUM, false>(p, ctas, sm, st, fma, a16, mg);
