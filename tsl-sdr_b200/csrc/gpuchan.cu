@@ -694,9 +694,9 @@ extern "C" int gpuchan_create(gpuchan_t **ph, const gpuchan_cfg *cfg)
         }
     }
     if (getenv("GPUCHAN_VERBOSE") && h->engine == GPUCHAN_ENGINE_TC)
-        fprintf(stderr, "gpuchan: tensor-core engine, tap limbs by %s (%d MMAs per 64-output tile, %d channel group%s, %d sample stages)\n",
+        fprintf(stderr, "gpuchan: tensor-core engine, tap limbs by %s (%d MMAs per 64-output tile, %d channel group%s, %d per CTA, %d sample stages)\n",
                 h->tc.mode == TC_MODE_SUM ? "sum of int8 terms" : "radix 256", (int)h->tc.prog.size(), h->tc.G, h->tc.G == 1 ? "" : "s",
-                h->tc.nb_stages);
+                h->tc.gpc, h->tc.nb_stages);
 
     /* --- pick the IMAD kernel variant that fits shared memory (also the fallback engine) --- */
     if (h->engine == GPUCHAN_ENGINE_IMAD) {
