@@ -408,9 +408,9 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
          * own channel x 8 outputs -- no shuffles, no selects.
          * The arithmetic (fm_math.cuh "v2") is arranged for the pipe split of sm_100: ncu showed the first
          * epilogue bound by the ALU pipe (67 % busy, FMA pipe 24 %), so selects/compares became multiply-adds. */
-        const int e = warp - EPI_WARP0;
+        const int e = warp_u - EPI_WARP0;           /* warp_u: provably warp-uniform, so the TMEM addresses stay in uniform registers */
         const int set = e >> 3;
-        const int slice = warp & 3;
+        const int slice = warp_u & 3;
         const int half = (e >> 2) & 1;
         const bool hi = lane >= 16;
         const int ch = 16 * slice + (lane & 15);
@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
             const int v = gpc == 2 ? 2 * it + set : it;         /* virtual tile: which accumulator stage holds it */
             const int st = v % NT, pht = (v / NT) & 1;
             const int cwk = cwk_next;
+            const bool tile_inside = TC_OUT * (tile + 1) < K32;
             ptx::mbar_wait_backoff(&t_full[st], pht, SLEEP_EPI);
             ptx::tc_fence_after();
             const uint32_t col0 = tmem_base + (uint32_t)st * STAGE_COLS + TC_LEAD + 32 * half;
@@ -528,7 +529,9 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
                 }
 
                 /* ---- one channel x 8 consecutive outputs ---- */
-                const int nvalid = (K32 - kfirst > 8) ? 8 : K32 - kfirst;
+                /* tile_inside (warp-uniform): every block of this tile is complete and none holds the submit's last output --
+                 * all tiles but the last one or two skip the per-thread edge bookkeeping */
+                const int nvalid = tile_inside ? 8 : ((K32 - kfirst > 8) ? 8 : K32 - kfirst);
                 if (TC_DIAG & 1) {
                     if (live && kfirst + 8 < K32) {
                         int acc = 0;
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
                         /* the thread that produced the submit's last output hands y[K-1] to the next submit */
                         if (EDGE) { if (kfirst + nvalid == K32) p.last_out[c] = pack16(l_re, l_im); }
                     };
-                    if (kfirst + 8 < K32) block8(std::false_type{});
+                    if (tile_inside || kfirst + 8 < K32) block8(std::false_type{});
                     else block8(std::true_type{});
                 }
             }
