@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
         const bool live = c < p.C;
         const int K32 = (int)p.K;                   /* outputs per channel of this submit (tc_launch_fir_fm checks the range) */
         const int iw = live ? __ldg(p.incr + c) : 0;
-        const int i4_re = 4 * lo16(iw), i4_im = 4 * hi16(iw);
+        const int i4_re = 4 * lo16(iw), i4_im = 4 * hi16(iw), ni4_im = -i4_im;
         short *const pcm_c = p.pcm + (size_t)c * p.pitch;
         int *const iq_c = KEEP_IQ ? p.iq_out + (size_t)c * p.pitch : nullptr;
         const float z_thr = p.atan.z_small_thr;
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
                     } else {
                         /* previous output = the column before my block; the phase word is its phase */
                         derotate_v2(comb(l0r, l1r, l2r) >> 16, comb(l0i, l1i, l2i) >> 16, r_re, r_im, p_re, p_im);
-                        rot_step_v2(r_re, r_im, i4_re, i4_im);
+                        rot_step_v2(r_re, r_im, i4_re, i4_im, ni4_im);
                     }
                 } else {
                     drain8(col0 + 8, x_re, x_im);
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(tc_threads(XF_WARPS), 1) tc_fir_fm_kernel(cons
                                 const int u = 4 * g4 + v;
                                 int y_re, y_im;
                                 derotate_v2(x_re[u] >> 16, x_im[u] >> 16, r_re, r_im, y_re, y_im);
-                                rot_step_v2(r_re, r_im, i4_re, i4_im);
+                                rot_step_v2(r_re, r_im, i4_re, i4_im, ni4_im);
                                 sre[v] = (int)((unsigned)y_re * (unsigned)p_re + (unsigned)y_im * (unsigned)p_im);    /* y * conj(prev) */
                                 sim[v] = (int)((unsigned)y_im * (unsigned)p_re - (unsigned)y_re * (unsigned)p_im);
                                 if (KEEP_IQ) { if (!EDGE || u < nvalid) iq_c[kfirst + u] = pack16(y_re, y_im); }
