@@ -18,17 +18,20 @@
  *   RADIX (any int16 taps): v = 256*hi + lo, four products per K chunk into three accumulators (2^16, 2^8, 1).
  * Only the K chunks a block-row really covers are issued (the last block-row of the filter is usually short).
  *
- * Kernel tc_fir_fm_kernel: persistent, warp specialised (26 warps):
- *   warps 0-15  epilogue, two sets of 8 on alternate tiles: drain TMEM (LDTM, shape 16x32bx2: both components of a
- *               thread's own columns) straight into registers, recombine the limbs, and run the exact rq /
- *               derotator recurrence / discriminator (fm_math.cuh); every thread owns 16 consecutive outputs of one
- *               channel = two 16-byte PCM stores.  No shared-memory staging, no shuffles and no CTA-wide barriers:
- *               a tile's 16 lead-in columns make it self-contained.
- *   warps 16-23 transform: read the raw cs16 tile from HBM/L2 and split it into two byte planes (hi s8 / lo u8) in
+ * Kernel tc_fir_fm_kernel: persistent, warp specialised (24 or 26 warps):
+ *   warps 0-15  epilogue, two sets of 8: drain TMEM (LDTM, shape 16x32bx2: both components of a thread's own columns)
+ *               straight into registers, recombine the limbs, and run the exact rq / derotator recurrence /
+ *               discriminator (fm_math.cuh); every thread owns 16 consecutive outputs of one channel = two 16-byte PCM
+ *               stores.  No shared-memory staging, no shuffles and no CTA-wide barriers: a tile's 16 lead-in columns
+ *               make it self-contained.  With one channel group per CTA the sets take alternate tiles; with two groups
+ *               per CTA (TcPlan::gpc = 2) set s owns group s and takes every tile.
+ *   next 6 or 8 transform: read the raw cs16 tile from HBM/L2 and split it into two byte planes (hi s8 / lo u8) in
  *               "slab" order [16-byte K slab][block-row][16 B] (rows zero padded to Kp = round_up(2D, 32) bytes)
  *               directly in an NB-stage shared-memory ring, one warp group per stage;
- *   warps 24-25 issue the tile's MMA program (tcgen05.mma kind::i8, SASS UTCIMMA) into an NT-stage TMEM ring, each
- *               warp the MMAs of its own limb accumulators.
+ *   last 2      issue the tile's MMA program (tcgen05.mma kind::i8, SASS UTCIMMA) into an NT-stage TMEM ring, each
+ *               warp the MMAs of its own limb accumulators.  With two groups per CTA every sample stage is used twice
+ *               in a row (virtual tile 2 * tile + group: the other group's tap image, the next accumulator stage).
+ *   The tap images (A operand, constant for the whole kernel) come in by one TMA bulk copy per CTA.
  * The B operand needs no im2col: with K-major / no-swizzle descriptors the Q row shifts are just +16 B on the
  * operand start address (validated by tc_selftest.cu).
  */
