@@ -545,8 +545,8 @@ def main():
                          "int16_mac_per_s": macs16 / (kern_avg_ms * 1e-3),
                          "int8_mac_issued_per_s": i8_issued / (kern_avg_ms * 1e-3),
                          "mac_frac": i8_issued / (kern_avg_ms * 1e-3) / i8pk, "mac_peak_int8_per_s": i8pk, "mac_peak_source": i8src,
-                         "note": "the path is bound by the SM's instruction issue for the exact derotate/atan2/PCM epilogue "
-                                 "(DESIGN.md 5.2), not by HBM or by the tensor pipe: both fractions are reported as required"},
+                         "note": "the path is bound by the exact derotate/atan2/PCM epilogue -- FMA-pipe cycles, issue slots and the register "
+                                 "file (DESIGN.md 5.2) -- not by HBM or by the tensor pipe: both fractions are reported as required"},
         }
         if not args.no_cpu_baseline and world == 1:
             try:
