@@ -189,7 +189,8 @@ int gpuchan_tc_selftest(const uint8_t *A0, const uint8_t *B0, const uint8_t *A1,
 /* Unit hook for tests, host only (works without a device): the tensor-core engine's plan for a configuration.
  * info[16] = { ok, mode (0 sum / 1 radix), accumulators, sample stages, TMEM stages, tap-image chunks, bytes per group
  * image, bytes per sample stage, dynamic shared memory, arctangent table copies, MMAs per tile, first MMA of the second
- * issuing warp, Kp, Q, R, channel groups }; tap_image (optional) receives [G][chunk][2][128][16] int8 limbs; program
+ * issuing warp, Kp, Q, R, channel groups | channel groups per CTA << 16 }; tap_image (optional) receives
+ * [G][chunk][2][128][16] int8 limbs; program
  * (optional) receives 4 words per MMA { a_lo, b_lo, d_acc, idesc } (csrc/tc_engine.cuh).  smem_max_bytes = 0: B200. */
 int gpuchan_tc_plan_query(const gpuchan_cfg *cfg, uint32_t smem_max_bytes, uint32_t info[16],
                           uint8_t *tap_image, size_t tap_image_cap, uint32_t *program, size_t program_cap_entries);

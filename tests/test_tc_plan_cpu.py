@@ -35,7 +35,7 @@ def plan(pkg, lpf, offs, fs, D, gains=None, smem=0):
     rc = L.gpuchan_tc_plan_query(C.byref(cfg), smem, info, None, 0, None, 0)
     if rc != 0:
         return rc, list(info), None, None
-    img = np.zeros(info[15] * info[6], np.uint8)
+    img = np.zeros((info[15] & 0xffff) * info[6], np.uint8)
     prog = np.zeros((info[10], 4), np.uint32)
     rc = L.gpuchan_tc_plan_query(C.byref(cfg), smem, info, img.ctypes.data, img.size, prog.ctypes.data, len(prog))
     assert rc == 0
@@ -101,6 +101,9 @@ def test_mma_program_equals_direct_integer_fir(pkg, Cn, T, D, fs, gains):
     rc, info, img, prog = plan(pkg, lpf, offs, fs, D, gains)
     assert rc == 0 and info[0] == 1
     ok, mode, accs, nb, nt, a_chunks, a_group_bytes, b_stage_bytes, smem, copies, prog_len, split, Kp, Q, R, G = info
+    G, gpc = G & 0xffff, G >> 16
+    assert gpc in (1, 2) and (gpc == 1 or (G % 2 == 0 and nb >= 2 and copies == 16))
+    assert smem == gpc * a_group_bytes + nb * b_stage_bytes + 2048 * copies + 128
     maxabs = max(int(np.abs(v).max()) for c in range(Cn)
                  for v in pkg.prepare_taps(lpf, offs[c], fs, 1.0 if gains is None else gains[c]))
     assert mode == (0 if maxabs <= 4 * 127 else 1)      # sum of at most four int8 terms, else radix 256
@@ -145,3 +148,23 @@ def test_plan_limits(pkg):
     assert rc == 0 and rc2 == 0
     assert full[9] == 16 and full[3] >= 3          # 16 conflict-free table copies and at least 3 stages on a B200
     assert tight[9] == 1 and 2 <= tight[3] <= full[3] and tight[8] <= 140000
+
+
+def test_two_channel_groups_per_cta_when_both_tap_images_fit(pkg, monkeypatch):
+    """TcPlan::gpc (csrc/tc_engine.cu tc_make_plan): a transformed sample tile feeds two channel groups' MMAs whenever both
+    tap images, two sample stages and the 16 arctangent copies fit the 227 KB; one group per CTA otherwise (odd group
+    counts, long filters) and under the measurement knob GPUCHAN_TC_GPC=1."""
+    def gpc_of(Cn, T, D, fs):
+        rc, info, _, _ = plan(pkg, synth.lowpass_taps(T, min(9000.0, fs / 8), fs), synth.channel_offsets(Cn, fs), fs, D)
+        assert rc == 0 and info[0] == 1
+        return int(info[15]) >> 16, int(info[3]), int(info[9]), int(info[8])
+    monkeypatch.delenv("GPUCHAN_TC_GPC", raising=False)
+    gpc, nb, copies, smem = gpc_of(256, 127, 100, 2400000)          # north_star's shape
+    assert (gpc, nb, copies) == (2, 2, 16) and smem <= 232448 - 3072
+    assert gpc_of(256, 127, 25, 1200000)[0] == 2                     # configs[2]
+    assert gpc_of(64, 127, 100, 2400000)[0] == 1                     # one group
+    assert gpc_of(192, 127, 100, 2400000)[0] == 1                    # three groups
+    assert gpc_of(1024, 255, 200, 10000000)[0] == 1                  # configs[3]: two 100 KB tap images do not fit
+    assert gpc_of(256, 512, 120, 3000000)[0] == 1                    # configs[4]
+    monkeypatch.setenv("GPUCHAN_TC_GPC", "1")
+    assert gpc_of(256, 127, 100, 2400000)[0] == 1

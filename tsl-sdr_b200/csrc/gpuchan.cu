@@ -573,7 +573,7 @@ extern "C" int gpuchan_tc_plan_query(const gpuchan_cfg *cfg, uint32_t smem_max_b
     info[5] = (uint32_t)pl.a_chunks; info[6] = (uint32_t)pl.a_group_bytes; info[7] = (uint32_t)pl.b_stage_bytes;
     info[8] = (uint32_t)pl.smem_bytes; info[9] = (uint32_t)pl.atan_copies; info[10] = (uint32_t)pl.prog.size();
     info[11] = (uint32_t)pl.prog_split; info[12] = (uint32_t)pl.Kp; info[13] = (uint32_t)pl.Q; info[14] = (uint32_t)pl.R;
-    info[15] = (uint32_t)pl.G;
+    info[15] = (uint32_t)pl.G | ((uint32_t)pl.gpc << 16);
     if (tap_image) {
         std::vector<uint8_t> img;
         tc_build_tap_image(pl, re.data(), im.data(), img);
