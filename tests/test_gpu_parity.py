@@ -179,6 +179,38 @@ def test_steady_state_window_tables(oracle, keep_iq):
             assert np.array_equal(np.concatenate(yiq, axis=1)[c], y.reshape(-1, 2))
 
 
+def test_steady_state_two_channel_groups_per_cta(oracle, pkg):
+    """128 channels = two channel groups sharing every transformed sample tile (TcPlan::gpc = 2: each epilogue set owns one
+    group), past every channel's derotator transient (phases from the cycle tables, one launch per submit), ragged submits.
+    Every channel's PCM against the oracle (filter/direct_fir.c:329-417, multifm/fm_demod.c:36-85)."""
+    from test_tc_plan_cpu import plan
+    C, T, D, fs = 128, 16, 4, 2400000
+    bad = {258750, 191250, 108750, 41250}          # offsets whose derotator transient is longer than the first submit
+    offs = np.array([k * 3750 for k in range(-68, 76) if abs(k * 3750) not in bad][:C], dtype=np.int32)
+    lpf = synth.lowpass_taps(T, 100000.0, fs)
+    rc, info, _, _ = plan(pkg, lpf, offs, fs, D)
+    assert rc == 0 and int(info[15]) >> 16 == 2, "this shape is meant to run with two groups per CTA"
+    chunks = [500001, 123457, 77777, 200003, 99999]
+    iq = rand_iq(sum(chunks), seed=78, amp=9000)
+    bank = GpuChan(lpf, offs, fs, D, max(chunks), flags=F_ATAN_FMA, engine=ENGINE_TC)
+    pcm, per_submit, pos = [], [], 0
+    for c in chunks:
+        before = bank.kernel_launches
+        bank.submit(iq[2 * pos: 2 * (pos + c)])
+        pcm.append(bank.collect().copy())
+        per_submit.append(bank.kernel_launches - before)
+        pos += c
+    mus = [bank.rot_state(c)[3] for c in range(C)]
+    bank.close()
+    assert max(mus) < chunks[0] // D, "a transient outlasts the first submit"
+    assert per_submit[0] > 1 and per_submit[1:] == [1] * (len(chunks) - 1), per_submit
+    pcm = np.concatenate(pcm, axis=1)
+    for c, off in enumerate(offs):
+        _, p = oracle.channel(lpf, off, fs, D, iq)
+        bad_at = np.flatnonzero(p != pcm[c])
+        assert bad_at.size == 0, f"channel {c} (offset {off}): first PCM mismatch at output {bad_at[0]} of {len(p)}"
+
+
 def test_taps_match_oracle(oracle, pkg):
     fs, T = 2400000, 127
     lpf = synth.lowpass_taps(T, 9000.0, fs)
