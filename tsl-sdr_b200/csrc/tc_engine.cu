@@ -18,14 +18,14 @@
  *   RADIX (any int16 taps): v = 256*hi + lo, four products per K chunk into three accumulators (2^16, 2^8, 1).
  * Only the K chunks a block-row really covers are issued (the last block-row of the filter is usually short).
  *
- * Kernel tc_fir_fm_kernel: persistent, warp specialised (24 or 26 warps):
+ * Kernel tc_fir_fm_kernel: persistent, warp specialised (24 or 28 warps):
  *   warps 0-15  epilogue, two sets of 8: drain TMEM (LDTM, shape 16x32bx2: both components of a thread's own columns)
  *               straight into registers, recombine the limbs, and run the exact rq / derotator recurrence /
  *               discriminator (fm_math.cuh); every thread owns 16 consecutive outputs of one channel = two 16-byte PCM
  *               stores.  No shared-memory staging, no shuffles and no CTA-wide barriers: a tile's 16 lead-in columns
  *               make it self-contained.  With one channel group per CTA the sets take alternate tiles; with two groups
  *               per CTA (TcPlan::gpc = 2) set s owns group s and takes every tile.
- *   next 6 or 8 transform: read the raw cs16 tile from HBM/L2 and split it into two byte planes (hi s8 / lo u8) in
+ *   next 6 or 10 transform: read the raw cs16 tile from HBM/L2 and split it into two byte planes (hi s8 / lo u8) in
  *               "slab" order [16-byte K slab][block-row][16 B] (rows zero padded to Kp = round_up(2D, 32) bytes)
  *               directly in an NB-stage shared-memory ring, one warp group per stage;
  *   last 2      issue the tile's MMA program (tcgen05.mma kind::i8, SASS UTCIMMA) into an NT-stage TMEM ring, each
@@ -53,9 +53,11 @@ constexpr int EPI_WARPS = 16;
  * group per stage also keeps every barrier wait at most one phase behind (a parity wait cannot tell phases two apart).
  * Measured on B200 (profiles/r02_xf_warps_experiment.txt): when a transformed tile serves two channel groups (TcPlan::gpc
  * = 2) 6 warps are enough and leave the epilogue 80 registers (256 channels x 127 taps: 4 / 5 / 6 / 8 warps 0.2548 / 0.2520 /
- * 0.2493 / 0.2559 ms); with one group per CTA 8 warps are faster (64 channels: 0.088 against 0.090 ms; 1024 channels x 255
- * taps, D = 200: 0.822 against 0.861; 256 x 512 taps: 0.348 against 0.367); 5 warps in groups of 2, 2, 1 lose 25 %. */
-constexpr int XF_PAIRED = 6, XF_ONE_GROUP = 8;
+ * 0.2493 / 0.2559 ms); with one group per CTA more warps are faster (8 against 6: 64 channels 0.088 against 0.090 ms; 1024
+ * channels x 255 taps, D = 200: 0.822 against 0.861; 256 x 512 taps: 0.348 against 0.367) and 10 warps -- 28 in the CTA, still
+ * 72 registers per thread -- faster again (64 channels 0.0828 against 0.0868, 256 x 512 taps 0.3483 against 0.3530); 5 warps
+ * in groups of 2, 2, 1 lose 25 %. */
+constexpr int XF_PAIRED = 6, XF_ONE_GROUP = 10;
 /* Warp roles, lowest warp index first: epilogue | transform | MMA issuer. */
 constexpr int EPI_WARP0 = 0;            /* must be a multiple of 4: warp w may only read TMEM lanes 32*(w%4).. */
 constexpr int XF_WARP0 = EPI_WARPS;     /* first transform warp */
@@ -858,7 +860,8 @@ cudaError_t tc_launch_fir_fm(const TcPlan &pl, const TcBatch &b, cudaStream_t st
     p.atan_copies = pl.atan_copies;
     const size_t sm = pl.smem_bytes;
     /* 6 transform warps (80 registers for the epilogue) when a transformed tile serves two groups, 8 otherwise (measured:
-     * profiles/r02_xf_warps_experiment.txt).  GPUCHAN_TC_XF=6|8 overrides the choice for measurements. */
+     * profiles/r02_xf_warps_experiment.txt).  GPUCHAN_TC_XF=6|8 (8 = the one-group form, now 10 warps)
+     * overrides the choice for measurements. */
     bool mg = pl.gpc == 2;
     if (const char *e = getenv("GPUCHAN_TC_XF")) { if (atoi(e) == 6) mg = true; else if (atoi(e) == 8) mg = false; }
     const bool a16 = pl.atan_copies == 16;
