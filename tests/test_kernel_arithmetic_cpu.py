@@ -1,14 +1,19 @@
-"""CPU: the fused kernel's FP64-free PCM scaling (csrc/fm_math.cuh pcm_from_phi_pair: two-float product of six
-multiply-adds, guard band as one multiply-add on the exponent of the rounded value, FP64 quotient by reciprocal with
-exact-remainder correction behind it) restated with exact rational arithmetic and checked against the reference's
-expression `(int16_t)(float)((double)phi / M_PI * 16384.0)` (multifm/fm_demod.c:71-72).
+"""CPU: the fused kernel's re-formulated discriminator arithmetic (csrc/fm_math.cuh) restated operation by operation in
+exact rational arithmetic with IEEE rounding, and checked against the reference's semantics:
 
-The exhaustive check -- every float in [-3.2, 3.2] through the device code -- is tests/test_gpu_math.py; this test pins
-the *formulas* without a GPU: random angles, and angles constructed to fall next to float rounding boundaries of the
-scaled value, where the guard band has to fire."""
+* the FP64-free PCM scaling (pcm_from_phi_pair: two-float product of six multiply-adds, guard band as one multiply-add
+  on the exponent of the rounded value, FP64 quotient by reciprocal with exact-remainder correction behind it) against
+  `(int16_t)(float)((double)phi / M_PI * 16384.0)` (multifm/fm_demod.c:71-72);
+* the branch-free arctangent (atan2p_stage1..3: division by reciprocal and five multiply-adds, floor by the 2^23 trick,
+  octant fix-up as multiply-adds on 0/1 compare results) against the oracle's transcription of
+  multifm/fast_atan2f.c:101-174 -- itself pinned to the reference objects by tests/test_oracle_vs_ref.py.
+
+The exhaustive checks -- every float in [-3.2, 3.2] and 2^31 operand pairs through the device code -- are
+tests/test_gpu_math.py; these tests pin the *formulas* without a GPU."""
 from fractions import Fraction
 
 import numpy as np
+import pytest
 
 
 def rn(x: Fraction, p: int) -> Fraction:
@@ -135,3 +140,75 @@ def test_fast_pcm_scaling_equals_the_reference_expression_outside_the_guard_band
 def test_exact_path_equals_the_reference_expression_everywhere():
     for phi in _angles()[::3]:
         assert exact_path(phi) == reference(phi), float(phi)
+
+
+# ---- arctangent ---------------------------------------------------------------------------------------------------
+
+def rz(x: Fraction, p: int) -> Fraction:
+    """x rounded toward zero to a p-bit significand (add.rz)."""
+    if x == 0:
+        return Fraction(0)
+    s, a = (-1 if x < 0 else 1), abs(x)
+    e = a.numerator.bit_length() - a.denominator.bit_length()
+    if a < Fraction(2) ** e:
+        e -= 1
+    ulp = Fraction(2) ** (e - p + 1)
+    return s * int(a // ulp) * ulp
+
+
+PI_F = Fraction(float(np.float32(3.14159265358979323846)))
+HPI_F = Fraction(float(np.float32(1.57079632679489661923)))
+TINY = Fraction(float(np.float32(1.0e-30)))
+Z_THR = np.float32(0.003921569)
+if float(Z_THR) < 0.003921569:
+    Z_THR = np.nextafter(Z_THR, np.float32(np.inf))         # host_z_small_thr(): (double)z < 0.003921569 as a float compare
+Z_THR = Fraction(float(Z_THR))
+
+
+def atan2_v3(s_im: int, s_re: int, table, fma: bool, seed_ulps: int) -> Fraction:
+    """atan2p_stage1..3 for one half of a pair.  seed_ulps perturbs the reciprocal seed (MUFU.RCP is good to about one ulp;
+    the quotient must come out correctly rounded whatever the seed within that)."""
+    fy, fx = f32(Fraction(s_im)), f32(Fraction(s_re))            # I2FP.F32.S32
+    ya, xa = abs(fy), f32(abs(fx) + TINY)
+    num, den = min(ya, xa), max(ya, xa)
+    r0 = f32(1 / den)
+    r0 += seed_ulps * (r0 - f32(r0 * (1 - Fraction(2) ** -24)) or Fraction(0))  # neighbouring floats of the exact reciprocal
+    e = f32(1 - den * r0)
+    r = f32(r0 + r0 * e)
+    q = f32(num * r)
+    rem = f32(num - den * q)
+    z = f32(q + r * rem)
+    assert z == f32(num / den), (s_im, s_re, seed_ulps)         # the div.rn fast path is exact for these operands
+    alpha = f32(z * 255)
+    t = rz(alpha + 2 ** 23, 24)
+    idx = int(t - 2 ** 23) & 0xff
+    frac = f32(alpha - (t - 2 ** 23))
+    e_x = Fraction(float(table[idx]))
+    e_y = f32(Fraction(float(table[idx + 1])) - e_x)             # the table's slope entry: float difference of neighbours
+    ip = f32(e_y * frac + e_x) if fma else f32(e_x + f32(e_y * frac))
+    base = z if z < Z_THR else ip
+    sb = -base if s_re < 0 else base
+    w01 = 1 if xa > ya else 0
+    cnx = 1 if fx < -ya else 0
+    w = f32(Fraction(w01 * 2 - 1))
+    cst = f32(cnx * PI_F + f32(w01 * -HPI_F + HPI_F))
+    inner = f32(sb * w + cst)
+    return -inner if s_im < 0 else inner
+
+
+@pytest.mark.parametrize("fma", [1, 0])
+def test_branch_free_arctangent_equals_the_oracle(oracle, fma):
+    table = oracle.atan_table()
+    rng = np.random.default_rng(17 + fma)
+    pairs = [(0, 0), (0, 1), (1, 0), (0, -1), (-1, 0), (1, 1), (-1, -1), (1, -1), (-1, 1), (2**31 - 1, 2**31 - 1),
+             (-2**31, -2**31), (-2**31, 2**31 - 1), (2**31 - 1, 1), (1, 2**31 - 1), (255, 65025), (1, 255), (1, 254), (1, 256)]
+    big = rng.integers(-2**31, 2**31, (1500, 2), dtype=np.int64)
+    small = rng.integers(-2**31, 2**31, (1500, 2), dtype=np.int64) >> rng.integers(0, 31, (1500, 2))
+    near_diag = rng.integers(-2**20, 2**20, 500, dtype=np.int64)
+    pairs += [tuple(int(v) for v in p) for p in big] + [tuple(int(v) for v in p) for p in small]
+    pairs += [(int(a), int(a + d)) for a, d in zip(near_diag, rng.integers(-2, 3, 500))]
+    for n, (s_im, s_re) in enumerate(pairs):
+        want = Fraction(float(oracle.L.orc_fast_atan2f(np.float32(s_im), np.float32(s_re), fma)))
+        for seed in ((-1, 0, 1) if n % 8 == 0 else (0,)):
+            got = atan2_v3(s_im, s_re, table, bool(fma), seed)
+            assert got == want, (s_im, s_re, fma, seed, float(got), float(want))
