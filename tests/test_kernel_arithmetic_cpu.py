@@ -212,3 +212,45 @@ def test_branch_free_arctangent_equals_the_oracle(oracle, fma):
         for seed in ((-1, 0, 1) if n % 8 == 0 else (0,)):
             got = atan2_v3(s_im, s_re, table, bool(fma), seed)
             assert got == want, (s_im, s_re, fma, seed, float(got), float(want))
+
+
+# ---- integer part -------------------------------------------------------------------------------------------------
+
+def _rq14_ref(a):
+    """filter/complex.h:31-34 round_q30_q15 with "Q_15_SHIFT" = 14 (filter/filter.h:16) on a wrapping int32, truncated to int16."""
+    a = a.astype(np.int32)
+    return ((a >> 14) + ((a >> 13) & 1)).astype(np.int16).astype(np.int64)
+
+
+def _wrap32(v):
+    return ((v + 2**31) % 2**32 - 2**31).astype(np.int64)
+
+
+def _top16(v):
+    return _wrap32(v) >> 16
+
+
+def test_integer_reformulations_equal_the_reference_rounding():
+    """The epilogue folds the "<< 2" and the rounding constant of rq() into the multiply-adds that produce its argument
+    (fm_math.cuh top16 / derotate_v2 / rot_step_v2 with the negated increment, tc_engine.cu comb): identities modulo 2^32,
+    checked here on a million random operands including the int16 / int32 extremes."""
+    rng = np.random.default_rng(5)
+    n = 1 << 20
+    i16 = lambda: np.concatenate([rng.integers(-32768, 32768, n - 4), [-32768, 32767, -32768, 32767]]).astype(np.int64)
+    i32 = lambda: np.concatenate([rng.integers(-2**31, 2**31, n - 4), [-2**31, 2**31 - 1, 0, -1]]).astype(np.int64)
+    # rq14(a) == (4a + 0x8000) >> 16 for every wrapping int32 a
+    a = i32()
+    assert np.array_equal(_top16(4 * a + 0x8000), _rq14_ref(_wrap32(a)))
+    # limb recombination: SUM mode (a0 weight 2^8, a1 weight 1), RADIX mode (2^16, 2^8, 1)
+    a0, a1, a2 = i32(), i32(), i32()
+    assert np.array_equal(_top16(a1 * 4 + (a0 * 1024 + 0x8000)), _rq14_ref(_wrap32(a0 * 256 + a1)))
+    assert np.array_equal(_top16(a2 * 4 + (a1 * 1024 + (a0 * 262144 + 0x8000))), _rq14_ref(_wrap32(a0 * 65536 + a1 * 256 + a2)))
+    # derotation y = rq(q * rot) (direct_fir.c:162-163) and recurrence rot <- rq(rot * incr) (:166-167)
+    q_re, q_im, r_re, r_im, i_re, i_im = i16(), i16(), i16(), i16(), i16(), i16()
+    d_re, d_im = _wrap32(q_re * r_re - q_im * r_im), _wrap32(q_re * r_im + q_im * r_re)
+    assert np.array_equal(_top16(d_re * 4 + 0x8000), _rq14_ref(d_re)) and np.array_equal(_top16(d_im * 4 + 0x8000), _rq14_ref(d_im))
+    i4_re, i4_im, ni4_im = 4 * i_re, 4 * i_im, -4 * i_im
+    n_re = r_re * i4_re + (r_im * ni4_im + 0x8000)
+    n_im = r_re * i4_im + (r_im * i4_re + 0x8000)
+    assert np.array_equal(_top16(n_re), _rq14_ref(_wrap32(r_re * i_re - r_im * i_im)))
+    assert np.array_equal(_top16(n_im), _rq14_ref(_wrap32(r_re * i_im + r_im * i_re)))
